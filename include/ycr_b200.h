@@ -1,0 +1,182 @@
+/* ycr_b200.h — C ABI of the B200-native polar-contour hot path.
+ *
+ * The reference (ai4in/YOLO-Contour-Regression) is pure Python/PyTorch and has no FFI layer; its
+ * boundary for this path is the Python symbol surface listed in SURVEY.md §8(b).  Each entry point
+ * below replaces one of those symbols (cited as file:line under
+ * /root/reference/ultralytics-main/ultralytics/) and is what a ctypes / cffi / TORCH_LIBRARY stub on
+ * the reference side binds (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _h;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises the
+ *     host unless stated; inputs are never written;
+ *   - fp32 data, int32 indices unless stated; the *_i64 outputs exist because the reference API
+ *     returns int64 tensors;
+ *   - return value: 0 on success, a negative YCR_E_* code otherwise (never a CPU fallback);
+ *   - workspace is caller-provided; size it with the matching *_workspace_bytes() call.
+ */
+#ifndef YCR_B200_H
+#define YCR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YCR_MAX_LEVELS 4
+#define YCR_CONTOUR_POINTS 360 /* fixed by the reference wire format, utils/instance.py:202 */
+
+#define YCR_OK 0
+#define YCR_E_ARG (-1)       /* bad argument (shape, null pointer, unsupported R) */
+#define YCR_E_WORKSPACE (-2) /* workspace too small */
+#define YCR_E_CUDA (-3)      /* a CUDA call failed; see ycr_last_error() */
+
+/* Anchor grid: level-major, row-major (y outer), centres at (i+0.5)*stride — what
+ * make_anchors_polar (utils/tal.py:1393-1407) and Segment.make_anchors (nn/modules/head.py:445-459)
+ * produce. */
+typedef struct {
+    int n_levels;
+    int h[YCR_MAX_LEVELS];
+    int w[YCR_MAX_LEVELS];
+    float stride[YCR_MAX_LEVELS];
+} ycr_grid_t;
+
+/* A strided view of the head predictions, one entry per level, so that both layouts on the path are
+ * read in place without the reference's cat/permute copies (utils/loss.py:815-822):
+ *   raw head feats (B, R+nc, H_l, W_l):  rays = feat_l, cls = feat_l + R*H*W, sb = (R+nc)*H*W,
+ *                                         sa = 1, sc = H*W, ray_scale = stride_l, cls_is_logit = 1
+ *   assigner API tensors (B,A,R)/(B,A,nc): rays = pd_bboxes + off_l*R, sb = A*R, sa = R, sc = 1,
+ *                                         ray_scale = 1, cls_is_logit = 0
+ * element (b, a_local, c) of level l lives at ptr[l][b*sb + a_local*sa + c*sc]. */
+typedef struct {
+    const float* rays[YCR_MAX_LEVELS];
+    const float* cls[YCR_MAX_LEVELS];
+    int64_t rays_sb[YCR_MAX_LEVELS], rays_sa[YCR_MAX_LEVELS], rays_sc[YCR_MAX_LEVELS];
+    int64_t cls_sb[YCR_MAX_LEVELS], cls_sa[YCR_MAX_LEVELS], cls_sc[YCR_MAX_LEVELS];
+    float ray_scale[YCR_MAX_LEVELS];
+    int cls_is_logit;
+} ycr_pred_view_t;
+
+/* Padded ground truth, as v8DetectionLoss.preprocess emits it (utils/loss.py:215-239) and
+ * v8SegmentationLoss splits it (utils/loss.py:842-844).  Row (b,g) of each field lives at
+ * ptr[(b*G + g) * row_stride]; the split views of the packed (B,G,725) tensor have row_stride 725.
+ * mask_gt may be NULL, in which case valid(b,g) = (sum of the 4 box values > 0), utils/loss.py:844. */
+typedef struct {
+    int B, G;
+    const float* labels; int64_t labels_stride; /* 1 value: class id as float */
+    const float* boxes;  int64_t boxes_stride;  /* 4 values: xyxy px */
+    const float* coor;   int64_t coor_stride;   /* 720 values: x0,y0,x1,y1,... px */
+    const float* mask_gt; int64_t mask_stride;  /* 1 value or NULL */
+} ycr_gt_t;
+
+/* Assigner hyper-parameters, TaskAlignedAssigner.__init__ (utils/tal.py:1125); the live values are
+ * topk=10, alpha=0.5, beta=4.0 (utils/loss.py:210). */
+typedef struct {
+    int topk;
+    int num_classes;
+    int rays; /* 36 (reference) or 72 */
+    float alpha, beta, eps;
+} ycr_assign_cfg_t;
+
+/* Dense outputs of TaskAlignedAssigner.forward (utils/tal.py:1204).  Any pointer may be NULL to
+ * skip that output.  gt_dist/centerness rows are in (b,g,a) lexicographic order (utils/tal.py:1175)
+ * and must have room for B*G*topk rows... see ycr_assign: n_pos is returned in *n_pos_d. */
+typedef struct {
+    int64_t* target_labels_i64; /* (B,A) */
+    float* target_bboxes;       /* (B,A,4) */
+    float* target_scores;       /* (B,A,nc) */
+    uint8_t* mask_pos;          /* (B,G,A) bool */
+    int64_t* target_gt_idx_i64; /* (B,A) */
+    uint8_t* fg_mask;           /* (B,A) bool */
+    float* gt_dist;             /* (pos_capacity, R) */
+    float* centerness;          /* (pos_capacity) */
+    int pos_capacity;           /* rows available in gt_dist / centerness */
+    int* n_pos_d;               /* device int: number of positives P */
+    float* overlaps;            /* optional debug: (B,G,A), get_box_metrics_polar utils/tal.py:1237 */
+    float* align_metric;        /* optional debug: (B,G,A) */
+} ycr_assign_out_t;
+
+const char* ycr_last_error(void);
+int ycr_version(void);
+
+/* ---- training path --------------------------------------------------------------------------- */
+
+/* Upper bound of in-box candidates (sum over GTs of anchors inside the GT box) computed on the host
+ * from host copies of the boxes (B*G rows of xyxy px, row_stride floats apart).  Lets callers size
+ * the workspace without a device sync. */
+int64_t ycr_candidate_bound_h(const ycr_grid_t* grid, const float* boxes_h, int64_t row_stride, int n_rows);
+
+size_t ycr_assign_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg,
+                                  int64_t cand_capacity);
+
+/* Replaces TaskAlignedAssigner.forward (utils/tal.py:1135-1204): in-box candidates
+ * (utils/tal.py:52-66), polygon->polar targets + Polar-IoU per candidate (utils/tal.py:1237-1284,
+ * 1445-1464), per-GT top-k (utils/tal.py:1304-1338), multi-GT resolution (utils/tal.py:214-248),
+ * polar targets of the positives (utils/tal.py:1172-1193), targets and normalisation
+ * (utils/tal.py:1340-1390, 1197-1202). */
+int ycr_assign(const ycr_grid_t* grid, const ycr_pred_view_t* pred, const ycr_gt_t* gt,
+               const ycr_assign_cfg_t* cfg, const ycr_assign_out_t* out, void* workspace,
+               size_t workspace_bytes, int64_t cand_capacity, void* stream);
+
+/* Hyper-parameters of v8SegmentationLoss (utils/loss.py:876-877, cfg/default.yaml:89-90). */
+typedef struct {
+    float box_gain; /* hyp.box = 7.5 */
+    float cls_gain; /* hyp.cls = 0.5 */
+} ycr_loss_cfg_t;
+
+size_t ycr_seg_loss_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg,
+                                    int64_t cand_capacity);
+
+/* Replaces v8SegmentationLoss.__call__ (utils/loss.py:808-878) from the head feature maps on:
+ * assignment as above, BCE-with-logits class loss (utils/loss.py:866-867), Polar-IoU log-ratio loss
+ * (MaskIOULoss.forward utils/loss.py:113-127), gains, and — in the same pass — the gradient of the
+ * returned scalar `loss.sum()*B` with respect to every feature map element.
+ *   feats[l]      (B, R+nc, H_l, W_l) contiguous
+ *   grad_feats[l] same shape, fully overwritten (may be NULL for a forward-only call)
+ *   loss_out      device float[4]: {total = (l_box+l_cls)*B, l_box, l_cls, target_scores_sum} */
+int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, float* const* grad_feats,
+                         const ycr_gt_t* gt, const ycr_assign_cfg_t* acfg, const ycr_loss_cfg_t* lcfg,
+                         float* loss_out, void* workspace, size_t workspace_bytes, int64_t cand_capacity,
+                         void* stream);
+
+/* In-place grad *= *scale_d for the three gradient maps; returns immediately on the device when
+ * *scale_d == 1 (the common loss.backward() case), so autograd's upstream gradient costs no pass. */
+int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* grad_feats,
+                    const float* scale_d, void* stream);
+
+/* GT packing, replaces v8DetectionLoss.preprocess (utils/loss.py:215-239): `targets` rows exactly as
+ * utils/loss.py:839 concatenates them — [image index, class, x, y, w, h (normalised), 720 contour values
+ * (normalised)], row_stride floats apart, any order of images — -> padded (B,G,725) in px. */
+int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,
+                     float* out_packed, void* stream);
+
+/* ---- inference path -------------------------------------------------------------------------- */
+
+/* Replaces Segment.forward eval branch / distance2mask (nn/modules/head.py:461-494, 559-570):
+ * feats -> allpred (B, 4+nc+3R, A) = [box xyxy | sigmoid cls | x_0.. | y_0.. | valid_0..]. */
+int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred,
+               void* stream);
+
+typedef struct {
+    float conf_thres, iou_thres;
+    int agnostic, multi_label;
+    int max_det, nc, max_nms;
+    float max_wh;
+    const int* classes; int n_classes; /* optional device list of class ids to keep, utils/ops.py:390 */
+} ycr_nms_cfg_t;
+
+size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* cfg);
+
+/* Replaces ops.non_max_suppression, polar variant (utils/ops.py:285-424) including the
+ * torchvision.ops.nms step (utils/ops.py:407).  prediction (B, 4+nc+nm, A).
+ *   out_rows   (B, max_det, 6+nm): kept rows in descending-score order
+ *   out_counts (B) device int: rows kept per image */
+int ycr_nms(const float* prediction, int B, int channels, int A, const ycr_nms_cfg_t* cfg, float* out_rows,
+            int* out_counts, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YCR_B200_H */

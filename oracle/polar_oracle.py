@@ -192,15 +192,18 @@ def assign(pd_scores, pd_rays, anc_px, gt_labels, gt_boxes, mask_gt, gt_coor,
         "target_gt_idx": torch.zeros(B, A, dtype=torch.int64),
         "fg_mask": torch.zeros(B, A, dtype=torch.bool),
         "overlaps": torch.zeros(B, G, A),
+        "overlaps_lo": torch.zeros(B, G, A),
+        "overlaps_hi": torch.zeros(B, G, A),
         "align_metric": torch.zeros(B, G, A),
         "certain": torch.ones(B, dtype=torch.bool),
         "n_candidates": 0, "n_ambiguous_rays": 0,
     }
-    dist_rows, cent_rows = [], []
+    dist_rows, cent_rows, amb_rows = [], [], []
     if G == 0:
         out["target_labels"].fill_(nc)  # bg_idx, utils/tal.py:1159
         out["gt_dist"] = torch.zeros(0, R)
         out["centerness"] = torch.zeros(0)
+        out["gt_dist_ambiguous"] = torch.zeros(0, R, dtype=torch.bool)
         return out
     for b in range(B):
         boxes = gt_boxes[b]                                    # (G,4)
@@ -270,6 +273,7 @@ def assign(pd_scores, pd_rays, anc_px, gt_labels, gt_boxes, mask_gt, gt_coor,
             ptp = polar_targets(anc_px[pa], contour[pg], R, tol_deg=tol_deg)
             dist_rows.append(ptp["t"])
             cent_rows.append(centerness(ptp["t"]))
+            amb_rows.append(ptp["ambiguous"])
         # --- get_targets ---
         labels = gt_labels[b, :, 0].long()[tgi].clamp(min=0)
         tboxes = boxes[tgi]
@@ -289,10 +293,13 @@ def assign(pd_scores, pd_rays, anc_px, gt_labels, gt_boxes, mask_gt, gt_coor,
         out["target_gt_idx"][b] = tgi
         out["fg_mask"][b] = fg > 0
         out["overlaps"][b] = overlaps
+        out["overlaps_lo"][b] = ov_lo
+        out["overlaps_hi"][b] = ov_hi
         out["align_metric"][b] = align
         out["certain"][b] = certain
     out["gt_dist"] = torch.cat(dist_rows) if dist_rows else torch.zeros(0, R)
     out["centerness"] = torch.cat(cent_rows) if cent_rows else torch.zeros(0)
+    out["gt_dist_ambiguous"] = torch.cat(amb_rows) if amb_rows else torch.zeros(0, R, dtype=torch.bool)
     return out
 
 

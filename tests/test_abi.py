@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/ycr_b200.h
+declares; host-only entry points behave; the product refuses to run without CUDA (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from util import ROOT
+import ycr_b200  # noqa: F401
+from ycr_b200 import _lib as L
+from ycr_b200 import build as B
+
+
+@pytest.fixture(scope="module")
+def lib():
+    B.build()
+    return L.lib()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "ycr_b200.h")).read()
+    declared = set(re.findall(r"\b(ycr_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    raw = C.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in the header but not exported"
+    assert declared == set(L.EXPORTS), "ctypes binding and header disagree"
+    assert lib.ycr_version() == 100
+
+
+def test_host_only_entry_points(lib):
+    g = L.make_grid([(80, 80), (40, 40), (20, 20)], [8, 16, 32])
+    boxes = torch.tensor([[100., 100., 260., 200.], [0., 0., 0., 0.], [10., 10., 630., 630.]])
+    n = lib.ycr_candidate_bound_h(C.byref(g), boxes.data_ptr(), 4, 3)
+    exact = 0
+    for x1, y1, x2, y2 in boxes.tolist():
+        for (h, w), s in zip([(80, 80), (40, 40), (20, 20)], [8, 16, 32]):
+            xs = [(i + 0.5) * s for i in range(w)]
+            ys = [(i + 0.5) * s for i in range(h)]
+            exact += sum(x1 < x < x2 for x in xs) * sum(y1 < y < y2 for y in ys)
+    assert exact <= n <= exact * 1.6 + 64
+    cfg = L.AssignCfg(10, 80, 36, 0.5, 4.0, 1e-9)
+    a = lib.ycr_assign_workspace_bytes(C.byref(g), 2, 8, C.byref(cfg), 10000)
+    b = lib.ycr_seg_loss_workspace_bytes(C.byref(g), 2, 8, C.byref(cfg), 10000)
+    assert 0 < a < b < 64 << 20
+    bad = L.AssignCfg(10, 80, 35, 0.5, 4.0, 1e-9)
+    assert lib.ycr_assign_workspace_bytes(C.byref(g), 2, 8, C.byref(bad), 10000) == 0
+    assert b"rays" in lib.ycr_last_error()
+    ncfg = L.NmsCfg(0.25, 0.7, 0, 0, 300, 80, 30000, 7680.0, None, 0)
+    assert lib.ycr_nms_workspace_bytes(4, 8400, 192, C.byref(ncfg)) > 0
+
+
+def test_argument_errors_without_gpu(lib):
+    g = L.make_grid([(20, 20)], [8])
+    rc = lib.ycr_decode(C.byref(g), None, 1, 10, 36, None, None)
+    assert rc == -1 and b"null" in lib.ycr_last_error()
+    ncfg = L.NmsCfg(1.5, 0.7, 0, 0, 300, 80, 30000, 7680.0, None, 0)
+    one = torch.zeros(8)
+    rc = lib.ycr_nms(one.data_ptr(), 1, 192, 100, C.byref(ncfg), one.data_ptr(), one.data_ptr(), one.data_ptr(), 8, None)
+    assert rc == -1 and b"thresholds" in lib.ycr_last_error()
+
+
+def test_no_cpu_fallback():
+    from ycr_b200.head import decode
+    from ycr_b200.ops import non_max_suppression
+    from ycr_b200.loss import v8SegmentationLoss
+    with pytest.raises(L.YcrError):
+        decode([torch.zeros(1, 46, 4, 4)], [8], 10, 36)
+    with pytest.raises(L.YcrError):
+        non_max_suppression(torch.zeros(1, 122, 16), nc=10)
+    crit = v8SegmentationLoss(nc=10, nm=36, strides=(8, 16, 32), device="cpu")
+    with pytest.raises(L.YcrError):
+        crit(([torch.zeros(1, 46, 4, 4)] * 3, 5, 2), {})
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "yolo-contour-regression_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|polar_oracle|oracle/", src, re.M), \
+                    f"{f} references the oracle"

@@ -1,0 +1,151 @@
+"""GPU parity tests of the inference path: Segment decode and non_max_suppression, through the
+C-ABI library via the host mirror, against reference-generated golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from util import load_golden, infer_inputs, split_rows
+from oracle import polar_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+NMS_CASES = (("best", dict(conf_thres=0.25, iou_thres=0.7, multi_label=False)),
+             ("multi", dict(conf_thres=0.25, iou_thres=0.7, multi_label=True)),
+             ("agn", dict(conf_thres=0.4, iou_thres=0.5, agnostic=True, max_det=50)))
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("name", ["infer_s160", "infer_s320", "infer_c3small"])
+def test_decode_matches_reference(name):
+    from ycr_b200.head import decode
+    dev = _dev()
+    g = load_golden(name)
+    cfg, feats = infer_inputs(g)
+    out = decode([f.to(dev) for f in feats], cfg.strides, cfg.nc, cfg.rays).cpu()
+    ref = po.decode(feats, cfg.strides, cfg.nc, cfg.rays)
+    if "allpred" in g:
+        assert np.array_equal(ref.numpy(), g["allpred"])
+    assert out.shape == ref.shape
+    # fp32 tolerance 1e-5 relative (+1e-5 px absolute for coordinates that cancel to ~0)
+    assert bool(((out - ref).abs() <= 1e-5 * ref.abs() + 1e-5).all())
+    R, nc = cfg.rays, cfg.nc
+    assert torch.equal(out[:, 4 + nc + 2 * R:], ref[:, 4 + nc + 2 * R:])      # validity flags: exact
+    frac_exact = float((out == ref).float().mean())
+    assert frac_exact > 0.95, frac_exact
+
+
+@pytest.mark.parametrize("name", ["infer_s160", "infer_s320", "infer_c3small"])
+def test_nms_matches_reference_keep_lists(name):
+    """NMS in isolation: feed the reference's own decoded tensor, expect identical rows."""
+    from ycr_b200.ops import non_max_suppression
+    dev = _dev()
+    g = load_golden(name)
+    cfg, feats = infer_inputs(g)
+    allpred = po.decode(feats, cfg.strides, cfg.nc, cfg.rays)
+    for tag, kw in NMS_CASES:
+        dets = non_max_suppression(allpred.to(dev), nc=cfg.nc, **kw)
+        assert [d.shape[0] for d in dets] == g[f"nms_{tag}_counts"].tolist(), tag
+        ref = split_rows(g[f"nms_{tag}_rows"], g[f"nms_{tag}_counts"])
+        for d, r in zip(dets, ref):
+            assert np.array_equal(d.cpu().numpy(), r), tag
+
+
+def test_decode_then_nms_pipeline():
+    """End to end on the product's own decode output: same keep-lists as the oracle pipeline."""
+    from ycr_b200.head import decode
+    from ycr_b200.ops import non_max_suppression
+    dev = _dev()
+    g = load_golden("infer_s320")
+    cfg, feats = infer_inputs(g)
+    out = decode([f.to(dev) for f in feats], cfg.strides, cfg.nc, cfg.rays)
+    dets = non_max_suppression(out, 0.25, 0.7, nc=cfg.nc)
+    ref, margin = po.nms(po.decode(feats, cfg.strides, cfg.nc, cfg.rays), 0.25, 0.7, nc=cfg.nc)
+    assert margin > 1e-5
+    assert [d.shape[0] for d in dets] == [r.shape[0] for r in ref]
+    for d, r in zip(dets, ref):
+        assert torch.equal(d[:, 5].cpu(), r[:, 5])
+        assert bool(((d.cpu() - r).abs() <= 1e-5 * r.abs() + 1e-5).all())
+
+
+def _random_pred(rng, B, A, nc, nm, n_hot, dup=False):
+    pred = np.zeros((B, 4 + nc + nm, A), np.float32)
+    xy = rng.uniform(0, 600, size=(B, 2, A)).astype(np.float32)
+    wh = rng.uniform(8, 160, size=(B, 2, A)).astype(np.float32)
+    pred[:, 0:2] = xy
+    pred[:, 2:4] = xy + wh
+    pred[:, 4:4 + nc] = rng.uniform(0, 0.2, size=(B, nc, A)).astype(np.float32)
+    for b in range(B):
+        hot = rng.choice(A, size=min(A, n_hot), replace=False)
+        cls = rng.integers(0, nc, size=hot.size)
+        pred[b, 4 + cls, hot] = rng.uniform(0.3, 1.0, size=hot.size).astype(np.float32)
+        # clusters of near-duplicates so suppression actually happens
+        for k in range(0, hot.size - 1, 2):
+            pred[b, 0:4, hot[k + 1]] = pred[b, 0:4, hot[k]] + rng.uniform(-6, 6, size=4).astype(np.float32)
+            pred[b, 4:4 + nc, hot[k + 1]] = 0.05
+            pred[b, 4 + cls[k], hot[k + 1]] = rng.uniform(0.3, 1.0)
+        if dup and hot.size > 4:
+            pred[b, :, hot[3]] = pred[b, :, hot[2]]          # identical box and equal score: input order wins
+    pred[:, 4 + nc:] = rng.standard_normal((B, nm, A)).astype(np.float32)
+    return torch.from_numpy(pred)
+
+
+@pytest.mark.parametrize("A,n_hot,kw", [
+    (2100, 300, dict(conf_thres=0.25, iou_thres=0.7)),
+    (2100, 0, dict(conf_thres=0.25, iou_thres=0.7)),                       # nothing passes: empty outputs
+    (8400, 2000, dict(conf_thres=0.25, iou_thres=0.45, max_det=300)),
+    (8400, 6000, dict(conf_thres=0.25, iou_thres=0.6, max_det=1000)),       # > 4096 candidates: global sort
+    (8400, 1500, dict(conf_thres=0.25, iou_thres=0.5, multi_label=True)),
+    (8400, 1500, dict(conf_thres=0.25, iou_thres=0.5, classes=[1, 3, 5])),
+    (8400, 1500, dict(conf_thres=0.25, iou_thres=0.5, classes=[0, 2], multi_label=True)),
+    (8400, 3000, dict(conf_thres=0.25, iou_thres=0.5, max_nms=1000)),
+    (8400, 1500, dict(conf_thres=0.25, iou_thres=0.5, agnostic=True)),
+])
+def test_nms_random_vs_oracle(A, n_hot, kw):
+    from ycr_b200.ops import non_max_suppression
+    dev = _dev()
+    rng = np.random.default_rng(A + n_hot)
+    nc, nm = 8, 12
+    pred = _random_pred(rng, 3, A, nc, nm, n_hot, dup=True)
+    ref, margin = po.nms(pred, nc=nc, **kw)
+    assert margin > 1e-6
+    dets = non_max_suppression(pred.to(dev), nc=nc, **kw)
+    assert [d.shape[0] for d in dets] == [r.shape[0] for r in ref]
+    for d, r in zip(dets, ref):
+        assert d.shape[1] == 6 + nm
+        assert torch.equal(d.cpu(), r)
+
+
+def test_nms_argument_errors():
+    from ycr_b200.ops import non_max_suppression
+    dev = _dev()
+    p = torch.zeros(1, 4 + 3 + 2, 16, device=dev)
+    with pytest.raises(AssertionError):
+        non_max_suppression(p, conf_thres=1.5)
+    with pytest.raises(AssertionError):
+        non_max_suppression(p, iou_thres=-0.1)
+    out = non_max_suppression((p, None), nc=3)   # tuple input accepted (utils/ops.py:333-334)
+    assert len(out) == 1 and out[0].shape == (0, 8)
+
+
+def test_segment_head_forward_contract():
+    """Segment.forward outputs: train -> (feats,5,2); eval -> (allpred,(feats,allpred,1))."""
+    from ycr_b200.head import Segment
+    dev = _dev()
+    torch.manual_seed(0)
+    head = Segment(nc=10, nm=36, ch=(32, 64, 128)).to(dev)
+    head.stride = torch.tensor([8., 16., 32.])
+    head.bias_init()
+    x = [torch.randn(2, c, s, s, device=dev) for c, s in ((32, 20), (64, 10), (128, 5))]
+    head.train()
+    feats, a, b = head([t.clone() for t in x])
+    assert (a, b) == (5, 2) and [tuple(f.shape) for f in feats] == [(2, 46, 20, 20), (2, 46, 10, 10), (2, 46, 5, 5)]
+    head.eval()
+    with torch.no_grad():
+        allpred, (feats2, allpred2, one) = head([t.clone() for t in x])
+    assert allpred.shape == (2, 4 + 10 + 108, 525) and one == 1 and allpred2 is allpred
+    ref = po.decode([f.cpu() for f in feats2], (8, 16, 32), 10, 36)
+    assert bool(((allpred.cpu() - ref).abs() <= 1e-5 * ref.abs() + 1e-5).all())

@@ -1,0 +1,159 @@
+// extern "C" surface declared in include/ycr_b200.h.  Thin argument checking + kernel sequencing;
+// no torch types, no CPU fallbacks.
+#include "train_path.cuh"
+#include <stdarg.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void ycr_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st);
+int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
+                        cudaStream_t st);
+int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, cudaStream_t st);
+size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg);
+int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
+               void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+static int check_common(const ycr_grid_t* grid, const ycr_assign_cfg_t* cfg, int B, int G) {
+    if (!grid || !cfg) { ycr_set_error("null grid/cfg"); return YCR_E_ARG; }
+    if (grid->n_levels < 1 || grid->n_levels > YCR_MAX_LEVELS) { ycr_set_error("n_levels %d out of range", grid->n_levels); return YCR_E_ARG; }
+    if (cfg->rays != 36 && cfg->rays != 72) { ycr_set_error("rays must be 36 or 72, got %d", cfg->rays); return YCR_E_ARG; }
+    if (cfg->topk < 1 || cfg->topk > 64) { ycr_set_error("topk %d out of range [1,64]", cfg->topk); return YCR_E_ARG; }
+    if (B < 1 || G < 0 || G > 255) { ycr_set_error("B=%d G=%d out of range (G<=255)", B, G); return YCR_E_ARG; }
+    return YCR_OK;
+}
+
+extern "C" {
+
+const char* ycr_last_error(void) { return g_err; }
+int ycr_version(void) { return 100; }
+
+int64_t ycr_candidate_bound_h(const ycr_grid_t* grid, const float* boxes_h, int64_t row_stride, int n_rows) {
+    int64_t total = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const float* bx = boxes_h + r * row_stride;
+        const double w = (double)bx[2] - bx[0], h = (double)bx[3] - bx[1];
+        if (!(w > 0) || !(h > 0)) continue;
+        for (int l = 0; l < grid->n_levels; ++l) {
+            int64_t cx = (int64_t)floor(w / grid->stride[l]) + 2, cy = (int64_t)floor(h / grid->stride[l]) + 2;
+            if (cx > grid->w[l]) cx = grid->w[l];
+            if (cy > grid->h[l]) cy = grid->h[l];
+            total += cx * cy;
+        }
+    }
+    return total;
+}
+
+size_t ycr_assign_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg, int64_t cand_capacity) {
+    if (check_common(grid, cfg, B, G)) return 0;
+    GridDev gd = make_grid_dev(grid);
+    return assign_ws_layout(nullptr, nullptr, gd, B, G, cfg->topk, cfg->rays, cand_capacity, false);
+}
+
+size_t ycr_seg_loss_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg, int64_t cand_capacity) {
+    if (check_common(grid, cfg, B, G)) return 0;
+    GridDev gd = make_grid_dev(grid);
+    return assign_ws_layout(nullptr, nullptr, gd, B, G, cfg->topk, cfg->rays, cand_capacity, true);
+}
+
+int ycr_assign(const ycr_grid_t* grid, const ycr_pred_view_t* pred, const ycr_gt_t* gt, const ycr_assign_cfg_t* cfg,
+               const ycr_assign_out_t* out, void* workspace, size_t workspace_bytes, int64_t cand_capacity, void* stream) {
+    if (!pred || !gt || !out || !workspace) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    int rc = check_common(grid, cfg, gt->B, gt->G);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AssignArgs a{};
+    a.grid = make_grid_dev(grid);
+    a.pred = *pred;
+    a.gt = *gt;
+    a.cfg = *cfg;
+    a.pc = make_polar_const(cfg->rays);
+    AssignWs ws;
+    const size_t need = assign_ws_layout(&ws, workspace, a.grid, gt->B, gt->G, cfg->topk, cfg->rays, cand_capacity, false);
+    if (need > workspace_bytes) { ycr_set_error("assign workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
+    if ((rc = launch_assign_core(a, ws, st))) return rc;
+    if ((rc = launch_positive_targets(a, ws, out->gt_dist, out->centerness, out->pos_capacity, out->n_pos_d, false, nullptr, st))) return rc;
+    return launch_assign_dense(a, ws, *out, st);
+}
+
+int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, float* const* grad_feats, const ycr_gt_t* gt,
+                         const ycr_assign_cfg_t* acfg, const ycr_loss_cfg_t* lcfg, float* loss_out, void* workspace,
+                         size_t workspace_bytes, int64_t cand_capacity, void* stream) {
+    if (!feats || !gt || !lcfg || !loss_out || !workspace) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    int rc = check_common(grid, acfg, gt->B, gt->G);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    AssignArgs a{};
+    a.grid = make_grid_dev(grid);
+    a.gt = *gt;
+    a.cfg = *acfg;
+    a.pc = make_polar_const(acfg->rays);
+    const int R = acfg->rays, nc = acfg->num_classes;
+    for (int l = 0; l < grid->n_levels; ++l) {
+        const int64_t hw = (int64_t)grid->h[l] * grid->w[l];
+        a.pred.rays[l] = feats[l];
+        a.pred.cls[l] = feats[l] + (int64_t)R * hw;
+        a.pred.rays_sb[l] = a.pred.cls_sb[l] = (int64_t)(R + nc) * hw;
+        a.pred.rays_sa[l] = a.pred.cls_sa[l] = 1;
+        a.pred.rays_sc[l] = a.pred.cls_sc[l] = hw;
+        a.pred.ray_scale[l] = grid->stride[l];
+    }
+    a.pred.cls_is_logit = 1;
+    AssignWs ws;
+    const size_t need = assign_ws_layout(&ws, workspace, a.grid, gt->B, gt->G, acfg->topk, R, cand_capacity, true);
+    if (need > workspace_bytes) { ycr_set_error("loss workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
+    if ((rc = launch_assign_core(a, ws, st))) return rc;
+    if ((rc = launch_positive_targets(a, ws, nullptr, nullptr, 0, nullptr, true, lcfg, st))) return rc;
+    return launch_loss_stream(a, ws, feats, grad_feats, *lcfg, loss_out, st);
+}
+
+int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* grad_feats, const float* scale_d, void* stream) {
+    if (!grid || !grad_feats || !scale_d) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    for (int l = 0; l < grid->n_levels; ++l) {
+        int rc = launch_scale(grad_feats[l], (int64_t)B * channels * grid->h[l] * grid->w[l], scale_d, st);
+        if (rc) return rc;
+    }
+    return YCR_OK;
+}
+
+int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,
+                     float* out_packed, void* stream) {
+    if (!out_packed || (N > 0 && !targets)) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (B < 1 || G < 0 || row_stride < 6 + 2 * YCR_C) { ycr_set_error("bad B/G/row_stride"); return YCR_E_ARG; }
+    if (G == 0) return YCR_OK;
+    return launch_pack_targets(targets, row_stride, N, B, G, img_w, img_h, out_packed, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, void* stream) {
+    if (!grid || !feats || !allpred) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
+    return launch_decode(grid, feats, B, nc, R, allpred, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* cfg) {
+    (void)channels;
+    if (!cfg) return 0;
+    return nms_workspace_bytes(B, A, cfg);
+}
+
+int ycr_nms(const float* prediction, int B, int channels, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
+            void* workspace, size_t workspace_bytes, void* stream) {
+    if (!prediction || !cfg || !out_rows || !out_counts || !workspace) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (cfg->conf_thres < 0.f || cfg->conf_thres > 1.f || cfg->iou_thres < 0.f || cfg->iou_thres > 1.f) {
+        ycr_set_error("thresholds must lie in [0,1]");
+        return YCR_E_ARG;
+    }
+    if (cfg->nc < 1 || 4 + cfg->nc > channels) { ycr_set_error("bad nc %d for %d channels", cfg->nc, channels); return YCR_E_ARG; }
+    return launch_nms(prediction, B, channels, A, cfg, out_rows, out_counts, workspace, workspace_bytes,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

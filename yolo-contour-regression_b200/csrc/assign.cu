@@ -1,0 +1,659 @@
+// Training path, assignment stage: in-box candidate rectangles (K0), polar targets + Polar-IoU +
+// align metric per candidate (K1), per-GT top-k (K2), per-image multi-GT resolution / targets /
+// normalisation (K3), polar targets (+ Polar-IoU loss and its gradient) of the positives (K4),
+// and the dense API outputs of TaskAlignedAssigner.forward.
+//
+// Reference: utils/tal.py:1135-1390, :52-66, :214-248, :1445-1464 (file:line under
+// /root/reference/ultralytics-main/ultralytics/).  No (B,G,A) float tensor is materialised.
+#include "train_path.cuh"
+
+#define K1_NT 64
+#define K3_NT 512
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+struct AnchorPos { int level, iy, ix, a_local; };
+
+__device__ __forceinline__ AnchorPos anchor_pos(const GridDev& g, int a) {
+    AnchorPos p;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+        if (k < g.n_levels && a >= g.off[k]) l = k;
+    p.level = l;
+    p.a_local = a - g.off[l];
+    p.iy = p.a_local / g.w[l];
+    p.ix = p.a_local - p.iy * g.w[l];
+    return p;
+}
+
+// candidate c of GT bg -> anchor (level-major, row-major inside each level's rectangle)
+__device__ __forceinline__ AnchorPos cand_anchor(const GridDev& g, const int4* rect, int c) {
+    AnchorPos p{0, 0, 0, 0};
+    for (int l = 0; l < g.n_levels; ++l) {
+        const int4 r = rect[l];
+        const int n = r.z * r.w;
+        if (c < n) {
+            const int yy = c / r.z;
+            p.level = l;
+            p.iy = r.y + yy;
+            p.ix = r.x + (c - yy * r.z);
+            p.a_local = p.iy * g.w[l] + p.ix;
+            return p;
+        }
+        c -= n;
+    }
+    return p;
+}
+
+// candidate index of anchor position p inside GT bg, or -1 when the anchor is not in the GT's box
+__device__ __forceinline__ int cand_index(const GridDev& g, const int4* rect, const AnchorPos& p) {
+    int base = 0;
+    for (int l = 0; l < p.level; ++l) base += rect[l].z * rect[l].w;
+    const int4 r = rect[p.level];
+    const int dx = p.ix - r.x, dy = p.iy - r.y;
+    if (dx < 0 || dy < 0 || dx >= r.z || dy >= r.w) return -1;
+    return base + dy * r.z + dx;
+}
+
+__device__ __forceinline__ float anchor_coord(int i, float stride) { return ((float)i + 0.5f) * stride; }
+
+// ------------------------------------------------------------------------------------------------
+// K0: candidate rectangles.  The in-box predicate of select_candidates_in_gts (utils/tal.py:52-66),
+// min(ax-x1, ay-y1, x2-ax, y2-ay) > 1e-9, is separable in x and y, so the candidate set of a GT on
+// each level is exactly a rectangle of grid cells, found with the same fp32 comparisons.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void axis_range(float lo_edge, float hi_edge, float stride, int n, int& first, int& count) {
+    const float eps = 1e-9f;
+    int lo = (int)floorf(lo_edge / stride - 0.5f);
+    lo = max(0, min(n, lo));
+    while (lo > 0 && (anchor_coord(lo - 1, stride) - lo_edge) > eps) --lo;
+    while (lo < n && !((anchor_coord(lo, stride) - lo_edge) > eps)) ++lo;
+    int hi = (int)ceilf(hi_edge / stride - 0.5f);
+    hi = max(-1, min(n - 1, hi));
+    while (hi < n - 1 && (hi_edge - anchor_coord(hi + 1, stride)) > eps) ++hi;
+    while (hi >= 0 && !((hi_edge - anchor_coord(hi, stride)) > eps)) --hi;
+    first = lo;
+    count = max(0, hi - lo + 1);
+}
+
+__global__ void __launch_bounds__(1024) k_gt_setup(GridDev grid, ycr_gt_t gt, AssignWs ws, int chunk) {
+    __shared__ int s_c[1024], s_k[1024];
+    const int BG = gt.B * gt.G;
+    const int per = (BG + 1023) / 1024;
+    const int t = threadIdx.x;
+    const int b0 = min(BG, t * per), b1 = min(BG, (t + 1) * per);
+    int sum_c = 0, sum_k = 0;
+    for (int bg = b0; bg < b1; ++bg) {
+        const float* bx = gt.boxes + (int64_t)bg * gt.boxes_stride;
+        const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+        bool valid = gt.mask_gt ? (gt.mask_gt[(int64_t)bg * gt.mask_stride] != 0.f) : ((x1 + y1 + x2 + y2) > 0.f);
+        int n = 0;
+        for (int l = 0; l < grid.n_levels; ++l) {
+            int fx = 0, cx = 0, fy = 0, cy = 0;
+            if (valid) {
+                axis_range(x1, x2, grid.stride[l], grid.w[l], fx, cx);
+                axis_range(y1, y2, grid.stride[l], grid.h[l], fy, cy);
+                if (cx == 0 || cy == 0) cx = cy = 0;
+            }
+            ws.rect[bg * YCR_MAX_LEVELS + l] = make_int4(fx, fy, cx, cy);
+            n += cx * cy;
+        }
+        ws.valid[bg] = valid ? 1 : 0;
+        ws.ncand[bg] = n;
+        sum_c += n;
+        sum_k += (n + chunk - 1) / chunk;
+    }
+    s_c[t] = sum_c;
+    s_k[t] = sum_k;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        int vc = 0, vk = 0;
+        if (t >= o) { vc = s_c[t - o]; vk = s_k[t - o]; }
+        __syncthreads();
+        s_c[t] += vc;
+        s_k[t] += vk;
+        __syncthreads();
+    }
+    int run_c = s_c[t] - sum_c, run_k = s_k[t] - sum_k;
+    for (int bg = b0; bg < b1; ++bg) {
+        ws.cand_off[bg] = run_c;
+        ws.chunk_off[bg] = run_k;
+        const int n = ws.ncand[bg];
+        run_c += n;
+        run_k += (n + chunk - 1) / chunk;
+    }
+    if (t == 1023) {
+        ws.cand_off[BG] = s_c[1023];
+        ws.chunk_off[BG] = s_k[1023];
+        ws.totals[0] = s_c[1023];
+        ws.totals[1] = s_k[1023];
+        if ((int64_t)s_c[1023] > ws.cand_cap) ws.err[0] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: one thread per in-box candidate (b,g,a): polar targets, Polar-IoU (MaskIOU utils/tal.py:1445),
+// align metric score^alpha * ov^beta (utils/tal.py:1281).  Persistent blocks walk the chunk list.
+// ------------------------------------------------------------------------------------------------
+template <int R, int NT>
+__device__ __forceinline__ void init_raydir(PolarSmem<R, NT>& sm, int tid) {
+    for (int i = tid; i < R; i += NT) {
+        const double ang = (double)(i * (360 / R)) * (3.14159265358979323846 / 180.0);
+        sm.raydir[i] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+}
+
+__device__ __forceinline__ float align_of(float score, float ov, float alpha, float beta) {
+    const float s = (alpha == 0.5f) ? sqrtf(score) : powf(score, alpha);
+    float o;
+    if (beta == 4.0f) { const float o2 = ov * ov; o = o2 * o2; }
+    else o = powf(ov, beta);
+    return s * o;
+}
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int BG = a.gt.B * a.gt.G;
+    const int T = ws.totals[1];
+    if (ws.err[0]) return;
+    init_raydir<R, NT>(sm, tid);
+    int cur_bg = -1;
+    for (int work = blockIdx.x; work < T; work += gridDim.x) {
+        int lo = 0, hi = BG;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (ws.chunk_off[mid] <= work) lo = mid; else hi = mid;
+        }
+        const int bg = lo;
+        __syncthreads();
+        if (bg != cur_bg) {
+            const float* cp = a.gt.coor + (int64_t)bg * a.gt.coor_stride;
+            float* dst = reinterpret_cast<float*>(sm.contour);
+            for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
+            cur_bg = bg;
+        }
+        if (tid == 0) sm.qcount = 0;
+        __syncthreads();
+        const int c = (work - ws.chunk_off[bg]) * NT + tid;
+        const bool active = c < ws.ncand[bg];
+        const int4* rect = ws.rect + bg * YCR_MAX_LEVELS;
+        AnchorPos ap{0, 0, 0, 0};
+        float ax = 0.f, ay = 0.f;
+        if (active) {
+            ap = cand_anchor(a.grid, rect, c);
+            ax = anchor_coord(ap.ix, a.grid.stride[ap.level]);
+            ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
+            polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
+        }
+        polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        __syncthreads();
+        polar_settle_queue<R, NT>(sm, a.pc, tid);
+        __syncthreads();
+        if (active) {
+            const int b = bg / a.gt.G;
+            const int l = ap.level;
+            const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+            const int64_t sc = a.pred.rays_sc[l];
+            const float rs = a.pred.ray_scale[l];
+            float smin = 0.f, smax = 0.f;
+#pragma unroll 4
+            for (int i = 0; i < R; ++i) {
+                const float p = rp[i * sc] * rs;
+                const float t = __uint_as_float(sm.list[i][tid].x);
+                smin += fmaxf(fminf(p, t), YCR_FLOOR);
+                smax += fmaxf(p, t);
+            }
+            const float ov = smin / smax;
+            const int label = (int)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
+            float score = a.pred.cls[l][(int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
+                                        (int64_t)label * a.pred.cls_sc[l]];
+            if (a.pred.cls_is_logit) score = 1.f / (1.f + expf(-score));
+            const int64_t m = (int64_t)ws.cand_off[bg] + c;
+            ws.cand_ov[m] = ov;
+            ws.cand_align[m] = align_of(score, ov, a.cfg.alpha, a.cfg.beta);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: per-GT top-k over its candidates, one warp per GT (select_topk_candidates utils/tal.py:1304).
+// Order: metric descending, anchor index ascending on ties (candidates are enumerated in anchor
+// order).  If fewer than topk candidates have a positive metric, torch.topk over the full anchor
+// axis pads with zero-metric anchors; with lowest-index tie-breaking an in-box zero-metric candidate
+// is picked iff fewer than (topk - n_pos) zero-metric anchors precede it.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_topk_per_gt(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bg = blockIdx.x * 4 + warp;
+    const int BG = a.gt.B * a.gt.G;
+    if (bg >= BG) return;
+    const int topk = a.cfg.topk;
+    int* sel = ws.sel + (int64_t)bg * topk;
+    const int n = ws.valid[bg] ? ws.ncand[bg] : 0;
+    const float* al = ws.cand_align + ws.cand_off[bg];
+    const int4* rect = ws.rect + bg * YCR_MAX_LEVELS;
+    float last_v = __int_as_float(0x7f800000);  // +inf
+    int last_c = -1;
+    int n_sel = 0;
+    for (int k = 0; k < topk && n > 0; ++k) {
+        float bv = 0.f;
+        int bc = 0x7fffffff;
+        for (int c = lane; c < n; c += 32) {
+            const float v = al[c];
+            const bool elig = (v > 0.f) && (v < last_v || (v == last_v && c > last_c));
+            if (elig && (v > bv)) { bv = v; bc = c; }  // ascending c: first maximum kept
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+        }
+        if (bc == 0x7fffffff) break;
+        if (lane == 0) {
+            const AnchorPos p = cand_anchor(a.grid, rect, bc);
+            sel[n_sel] = a.grid.off[p.level] + p.a_local;
+        }
+        ++n_sel;
+        last_v = bv;
+        last_c = bc;
+    }
+    if (n_sel < topk && n > 0) {
+        // zero-metric in-box candidates as topk fillers (rare)
+        const int want = topk - n_sel;
+        for (int c0 = 0; c0 < n && n_sel < topk; c0 += 32) {
+            const int c = c0 + lane;
+            const bool zero = (c < n) && (al[c] == 0.f);
+            unsigned ball = __ballot_sync(0xffffffffu, zero);
+            while (ball && n_sel < topk) {
+                const int src = __ffs(ball) - 1;
+                ball &= ball - 1;
+                const int cz = c0 + src;
+                int cnt = 0;  // positive-metric candidates before cz
+                for (int q = lane; q < cz; q += 32) cnt += (al[q] > 0.f) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                const AnchorPos p = cand_anchor(a.grid, rect, cz);
+                const int anchor = a.grid.off[p.level] + p.a_local;
+                if (anchor - cnt < want) {
+                    if (lane == 0) sel[n_sel] = anchor;
+                    ++n_sel;
+                }
+            }
+        }
+    }
+    for (int k = n_sel + lane; k < topk; k += 32) sel[k] = -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: one block per image.  Counts how many GTs picked each anchor, resolves anchors picked by
+// several GTs to the GT with the highest overlap over ALL in-box GTs (select_highest_overlaps
+// utils/tal.py:214-248), orders the positives (g,a)-lexicographically (utils/tal.py:1175), and
+// computes the normalised target score (utils/tal.py:1197-1202).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    const int G = a.gt.G, topk = a.cfg.topk, pos_cap = ws.pos_cap;
+    uint32_t* s_a = reinterpret_cast<uint32_t*>(smem_raw);          // [A]
+    int* s_pa = reinterpret_cast<int*>(s_a + A);                    // [pos_cap]
+    int* s_pg = s_pa + pos_cap;                                     // [pos_cap]
+    float* s_al = reinterpret_cast<float*>(s_pg + pos_cap);         // [pos_cap]
+    uint32_t* s_gal = reinterpret_cast<uint32_t*>(s_al + pos_cap);  // [G]
+    uint32_t* s_gov = s_gal + G;                                    // [G]
+    int* s_gcnt = reinterpret_cast<int*>(s_gov + G);                // [G]
+    int* s_gstart = s_gcnt + G;                                     // [G]
+    __shared__ int s_n;
+    __shared__ float s_red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < A; i += K3_NT) s_a[i] = 0;
+    for (int i = tid; i < G; i += K3_NT) { s_gal[i] = 0; s_gov[i] = 0; s_gcnt[i] = 0; }
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    for (int e = tid; e < G * topk; e += K3_NT) {
+        const int g = e / topk;
+        const int anchor = ws.sel[(int64_t)(b * G) * topk + e];
+        if (anchor >= 0) atomicAdd(&s_a[anchor], 0x10000u + (uint32_t)g);
+    }
+    __syncthreads();
+    int* pos_row = ws.pos_row + (int64_t)b * A;
+    for (int an = tid; an < A; an += K3_NT) {
+        const uint32_t v = s_a[an];
+        const int cnt = v >> 16;
+        pos_row[an] = -1;
+        if (cnt == 0) continue;
+        int g = v & 0xFFFFu;
+        if (cnt > 1) {
+            const AnchorPos p = anchor_pos(a.grid, an);
+            float best = 0.f;
+            g = 0;
+            for (int gg = 0; gg < G; ++gg) {
+                const int bg = b * G + gg;
+                if (!ws.valid[bg]) continue;
+                const int ci = cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, p);
+                if (ci < 0) continue;
+                const float ov = ws.cand_ov[ws.cand_off[bg] + ci];
+                if (ov > best) { best = ov; g = gg; }
+            }
+        }
+        const int idx = atomicAdd(&s_n, 1);
+        if (idx < pos_cap) { s_pa[idx] = an; s_pg[idx] = g; }
+        atomicAdd(&s_gcnt[g], 1);
+    }
+    __syncthreads();
+    const int n = min(s_n, pos_cap);
+    if (tid == 0) {
+        int run = 0;
+        for (int g = 0; g < G; ++g) { s_gstart[g] = run; run += s_gcnt[g]; }
+    }
+    __syncthreads();
+    int* o_anchor = ws.pos_anchor + (int64_t)b * pos_cap;
+    int* o_g = ws.pos_g + (int64_t)b * pos_cap;
+    float* o_norm = ws.pos_norm + (int64_t)b * pos_cap;
+    for (int p = tid; p < n; p += K3_NT) {
+        const int an = s_pa[p], g = s_pg[p];
+        const int64_t key = (int64_t)g * A + an;
+        int rank = 0;
+        for (int q = 0; q < n; ++q) rank += ((int64_t)s_pg[q] * A + s_pa[q] < key) ? 1 : 0;
+        o_anchor[rank] = an;
+        o_g[rank] = g;
+        pos_row[an] = rank;
+        const int bg = b * G + g;
+        float alv = 0.f, ovv = 0.f;
+        const int ci = ws.valid[bg] ? cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, anchor_pos(a.grid, an)) : -1;
+        if (ci >= 0) {
+            alv = ws.cand_align[ws.cand_off[bg] + ci];
+            ovv = ws.cand_ov[ws.cand_off[bg] + ci];
+        }
+        s_al[rank] = alv;
+        atomicMax(&s_gal[g], __float_as_uint(fmaxf(alv, 0.f)));
+        atomicMax(&s_gov[g], __float_as_uint(fmaxf(ovv, 0.f)));
+    }
+    __syncthreads();
+    float part = 0.f;
+    for (int r = tid; r < n; r += K3_NT) {
+        const int g = o_g[r];
+        const float norm = s_al[r] * __uint_as_float(s_gov[g]) / (__uint_as_float(s_gal[g]) + a.cfg.eps);
+        o_norm[r] = norm;
+        part += norm;
+    }
+    // fixed-shape tree: deterministic
+    part = warp_sum(part);
+    if ((tid & 31) == 0) s_red[tid >> 5] = part;
+    __syncthreads();
+    if (tid < 32) {
+        float v = (tid < K3_NT / 32) ? s_red[tid] : 0.f;
+        v = warp_sum(v);
+        if (tid == 0) { ws.tss_part[b] = v; ws.npos[b] = n; }
+    }
+    for (int g = tid; g < G; g += K3_NT) {
+        ws.gt_row_start[b * G + g] = s_gstart[g];
+        ws.gt_row_cnt[b * G + g] = min(s_gcnt[g], max(0, pos_cap - s_gstart[g]));
+    }
+}
+
+// image row bases and the loss normaliser target_scores_sum = max(sum, 1) (utils/loss.py:866)
+__global__ void k_finalize_counts(AssignWs ws, int B, int* img_base, float* tss, int* n_pos_d) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        double s = 0.0;
+        for (int b = 0; b < B; ++b) { img_base[b] = run; run += ws.npos[b]; s += (double)ws.tss_part[b]; }
+        img_base[B] = run;
+        tss[0] = fmaxf((float)s, 1.f);
+        tss[1] = (float)s;
+        if (n_pos_d) *n_pos_d = run;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: polar targets of the positives (utils/tal.py:1172-1193), centerness (utils/tal.py:1220), and,
+// for the fused loss, the Polar-IoU log-ratio term of MaskIOULoss (utils/loss.py:113-127) with its
+// gradient with respect to the raw ray outputs.  One block per GT.
+// ------------------------------------------------------------------------------------------------
+struct PosArgs {
+    float* gt_dist; float* centerness; int pos_capacity;
+    const int* img_base; const float* tss;
+    int with_loss; float box_gain;
+};
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                                          const PosArgs pa) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
+    const int bg = blockIdx.x, tid = threadIdx.x;
+    const int cnt = ws.gt_row_cnt[bg];
+    if (cnt == 0) return;
+    const int b = bg / a.gt.G;
+    init_raydir<R, NT>(sm, tid);
+    {
+        const float* cp = a.gt.coor + (int64_t)bg * a.gt.coor_stride;
+        float* dst = reinterpret_cast<float*>(sm.contour);
+        for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
+    }
+    const int row0 = ws.gt_row_start[bg];
+    const int base = pa.img_base[b];
+    for (int r0 = 0; r0 < cnt; r0 += NT) {
+        __syncthreads();
+        if (tid == 0) sm.qcount = 0;
+        __syncthreads();
+        const int r = r0 + tid;
+        const bool active = r < cnt;
+        const int row = row0 + r;
+        AnchorPos ap{0, 0, 0, 0};
+        float ax = 0.f, ay = 0.f;
+        if (active) {
+            ap = anchor_pos(a.grid, ws.pos_anchor[(int64_t)b * ws.pos_cap + row]);
+            ax = anchor_coord(ap.ix, a.grid.stride[ap.level]);
+            ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
+            polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
+        }
+        polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        __syncthreads();
+        polar_settle_queue<R, NT>(sm, a.pc, tid);
+        __syncthreads();
+        if (!active) continue;
+        const int grow = base + row;
+        float tmin = 3.4e38f, tmax = 0.f;
+        for (int i = 0; i < R; ++i) {
+            const float t = __uint_as_float(sm.list[i][tid].x);
+            tmin = fminf(tmin, t);
+            tmax = fmaxf(tmax, t);
+            if (pa.gt_dist && grow < pa.pos_capacity) pa.gt_dist[(int64_t)grow * R + i] = t;
+        }
+        if (pa.centerness && grow < pa.pos_capacity) pa.centerness[grow] = sqrtf(tmin / tmax);
+        if (pa.with_loss) {
+            const int l = ap.level;
+            const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+            const int64_t sc = a.pred.rays_sc[l];
+            const float rs = a.pred.ray_scale[l];
+            float smin = 0.f, smax = 0.f;
+            for (int i = 0; i < R; ++i) {
+                const float p = rp[i * sc] * rs;
+                const float t = __uint_as_float(sm.list[i][tid].x);
+                smin += fmaxf(fminf(p, t), YCR_FLOOR);
+                smax += fmaxf(p, t);
+            }
+            const float w = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
+            ws.pos_loss[(int64_t)b * ws.pos_cap + row] = logf(smax / smin) * w;
+            const float coef = w / pa.tss[0] * pa.box_gain * (float)a.gt.B * rs;
+            const float imax = 1.f / smax, imin = 1.f / smin;
+            float* gp = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
+            for (int i = 0; i < R; ++i) {
+                const float p = rp[i * sc] * rs;
+                const float t = __uint_as_float(sm.list[i][tid].x);
+                float g = 0.f;
+                if (p >= t) g += imax;                       // max() routes to pred (first index on ties)
+                if (p <= t && p >= YCR_FLOOR) g -= imin;     // min() routes to pred; clamp passes when >= floor
+                gp[i] = g * coef;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense API outputs of TaskAlignedAssigner.forward (get_targets utils/tal.py:1340-1390)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dense_targets(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                const ycr_assign_out_t out) {
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.y;
+    const int an = blockIdx.x * blockDim.x + threadIdx.x;
+    if (an >= A) return;
+    const int G = a.gt.G, nc = a.cfg.num_classes;
+    const int row = ws.pos_row[(int64_t)b * A + an];
+    const bool fg = row >= 0;
+    const int g = fg ? ws.pos_g[(int64_t)b * ws.pos_cap + row] : 0;
+    const int64_t i = (int64_t)b * A + an;
+    const int bg = b * G + g;
+    int64_t label = (int64_t)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
+    if (label < 0) label = 0;
+    if (out.target_gt_idx_i64) out.target_gt_idx_i64[i] = g;
+    if (out.fg_mask) out.fg_mask[i] = fg ? 1 : 0;
+    if (out.target_labels_i64) out.target_labels_i64[i] = label;
+    if (out.target_bboxes) {
+        const float* bx = a.gt.boxes + (int64_t)bg * a.gt.boxes_stride;
+        reinterpret_cast<float4*>(out.target_bboxes)[i] = make_float4(bx[0], bx[1], bx[2], bx[3]);
+    }
+    if (out.target_scores) {
+        float* ts = out.target_scores + i * nc;
+        for (int c = 0; c < nc; ++c) ts[c] = 0.f;
+        if (fg && label < nc) ts[label] = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
+    }
+    if (out.mask_pos && fg) out.mask_pos[((int64_t)b * G + g) * A + an] = 1;
+}
+
+__global__ void k_dense_metrics(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                float* overlaps, float* align) {
+    const int bg = blockIdx.x;
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    if (!ws.valid[bg]) return;
+    const int n = ws.ncand[bg];
+    const int4* rect = ws.rect + bg * YCR_MAX_LEVELS;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        const AnchorPos p = cand_anchor(a.grid, rect, c);
+        const int64_t o = (int64_t)bg * A + a.grid.off[p.level] + p.a_local;
+        if (overlaps) overlaps[o] = ws.cand_ov[ws.cand_off[bg] + c];
+        if (align) align[o] = ws.cand_align[ws.cand_off[bg] + c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, int G, int topk, int R,
+                        int64_t cand_cap, bool with_loss) {
+    WsAlloc al{reinterpret_cast<char*>(base), 0, 0};
+    const int BG = B * G, A = grid.off[YCR_MAX_LEVELS];
+    const int pos_cap = (G * topk > 0) ? G * topk : 1;
+    AssignWs w{};
+    w.rect = al.take<int4>((size_t)BG * YCR_MAX_LEVELS + 1);
+    w.ncand = al.take<int>(BG + 1);
+    w.cand_off = al.take<int>(BG + 1);
+    w.chunk_off = al.take<int>(BG + 1);
+    w.valid = al.take<uint8_t>(BG + 1);
+    w.totals = al.take<int>(2);
+    w.err = al.take<int>(1);
+    w.cand_align = al.take<float>((size_t)cand_cap + 1);
+    w.cand_ov = al.take<float>((size_t)cand_cap + 1);
+    w.sel = al.take<int>((size_t)BG * topk + 1);
+    w.npos = al.take<int>(B + 1);
+    w.pos_anchor = al.take<int>((size_t)B * pos_cap);
+    w.pos_g = al.take<int>((size_t)B * pos_cap);
+    w.pos_norm = al.take<float>((size_t)B * pos_cap);
+    w.pos_row = al.take<int>((size_t)B * A);
+    w.gt_row_start = al.take<int>(BG + 1);
+    w.gt_row_cnt = al.take<int>(BG + 1);
+    w.tss_part = al.take<float>(B + 1);
+    w.img_base = al.take<int>(B + 2);
+    w.tss = al.take<float>(2);
+    if (with_loss) {
+        w.pos_loss = al.take<float>((size_t)B * pos_cap);
+        w.pos_grad = al.take<float>((size_t)B * pos_cap * R);
+        w.n_bce_blocks = ((A + 255) / 256) * B;
+        w.bce_part = al.take<float>((size_t)w.n_bce_blocks + 1);
+    }
+    w.pos_cap = pos_cap;
+    w.cand_cap = cand_cap;
+    if (ws) *ws = w;
+    return align_up(al.off, 256);
+}
+
+template <int R>
+static int launch_k1(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
+    const size_t smem = sizeof(PolarSmem<R, K1_NT>);
+    YCR_CUDA_CHECK(cudaFuncSetAttribute(k_cand_overlaps<R, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    YCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cand_overlaps<R, K1_NT>, K1_NT, smem));
+    if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = YCR_NUM_SMS;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    k_cand_overlaps<R, K1_NT><<<sms * per_sm, K1_NT, smem, st>>>(a, ws);
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
+int launch_assign_core(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
+    const int B = a.gt.B, G = a.gt.G, BG = B * G;
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    YCR_CUDA_CHECK(cudaMemsetAsync(ws.err, 0, sizeof(int), st));
+    if (BG > 0) {
+        k_gt_setup<<<1, 1024, 0, st>>>(a.grid, a.gt, ws, K1_NT);
+        YCR_LAUNCH_CHECK();
+        int rc = (a.cfg.rays == 36) ? launch_k1<36>(a, ws, st) : launch_k1<72>(a, ws, st);
+        if (rc) return rc;
+        k_topk_per_gt<<<(BG + 3) / 4, 128, 0, st>>>(a, ws);
+        YCR_LAUNCH_CHECK();
+    }
+    const size_t smem3 = (size_t)A * 4 + (size_t)ws.pos_cap * 12 + (size_t)G * 16 + 64;
+    YCR_CUDA_CHECK(cudaFuncSetAttribute(k_resolve_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    k_resolve_image<<<B, K3_NT, smem3, st>>>(a, ws);
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
+int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_dist, float* centerness,
+                            int pos_capacity, int* n_pos_d, bool with_loss, const ycr_loss_cfg_t* lcfg,
+                            cudaStream_t st) {
+    const int B = a.gt.B, BG = B * a.gt.G;
+    int* img_base = ws.img_base;
+    float* tss = ws.tss;
+    k_finalize_counts<<<1, 32, 0, st>>>(ws, B, img_base, tss, n_pos_d);
+    YCR_LAUNCH_CHECK();
+    PosArgs pa{gt_dist, centerness, pos_capacity, img_base, tss, with_loss ? 1 : 0, lcfg ? lcfg->box_gain : 0.f};
+    if (BG == 0) return YCR_OK;
+    if (a.cfg.rays == 36) {
+        const size_t smem = sizeof(PolarSmem<36, K1_NT>);
+        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_positive_targets<36, K1_NT><<<BG, K1_NT, smem, st>>>(a, ws, pa);
+    } else {
+        const size_t smem = sizeof(PolarSmem<72, K1_NT>);
+        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<72, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_positive_targets<72, K1_NT><<<BG, K1_NT, smem, st>>>(a, ws, pa);
+    }
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
+int launch_assign_dense(const AssignArgs& a, const AssignWs& ws, const ycr_assign_out_t& out, cudaStream_t st) {
+    const int B = a.gt.B, G = a.gt.G, BG = B * G;
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    if (out.mask_pos) YCR_CUDA_CHECK(cudaMemsetAsync(out.mask_pos, 0, (size_t)BG * A, st));
+    dim3 grid((A + 255) / 256, B);
+    k_dense_targets<<<grid, 256, 0, st>>>(a, ws, out);
+    YCR_LAUNCH_CHECK();
+    if (out.overlaps || out.align_metric) {
+        if (out.overlaps) YCR_CUDA_CHECK(cudaMemsetAsync(out.overlaps, 0, (size_t)BG * A * 4, st));
+        if (out.align_metric) YCR_CUDA_CHECK(cudaMemsetAsync(out.align_metric, 0, (size_t)BG * A * 4, st));
+        k_dense_metrics<<<BG, 128, 0, st>>>(a, ws, out.overlaps, out.align_metric);
+        YCR_LAUNCH_CHECK();
+    }
+    return YCR_OK;
+}

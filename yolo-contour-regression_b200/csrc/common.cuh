@@ -1,0 +1,80 @@
+// Shared declarations for the sm_100a kernels of the polar-contour hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/ycr_b200.h"
+
+#define YCR_C YCR_CONTOUR_POINTS
+#define YCR_EMPTY 0xFFFFFFFFu
+#define YCR_FLOOR 1e-6f          // utils/tal.py:1189-1191,1275-1277,1455; nn/modules/head.py:480
+#define YCR_GATE_DEG 3.0         // utils/tal.py:1185,1270
+#define YCR_NUM_SMS 148
+
+void ycr_set_error(const char* fmt, ...);
+
+#define YCR_CUDA_CHECK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ycr_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return YCR_E_CUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+#define YCR_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            ycr_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return YCR_E_CUDA;                                                            \
+        }                                                                                 \
+    } while (0)
+
+// Device-side copy of the grid with prefix offsets.
+struct GridDev {
+    int n_levels;
+    int h[YCR_MAX_LEVELS], w[YCR_MAX_LEVELS];
+    int off[YCR_MAX_LEVELS + 1];  // anchor offset of each level; off[n_levels] = A
+    float stride[YCR_MAX_LEVELS];
+};
+
+static inline GridDev make_grid_dev(const ycr_grid_t* g) {
+    GridDev d{};
+    d.n_levels = g->n_levels;
+    int acc = 0;
+    for (int l = 0; l < YCR_MAX_LEVELS; ++l) {
+        d.off[l] = acc;
+        if (l < g->n_levels) {
+            d.h[l] = g->h[l];
+            d.w[l] = g->w[l];
+            d.stride[l] = g->stride[l];
+            acc += g->h[l] * g->w[l];
+        }
+    }
+    d.off[YCR_MAX_LEVELS] = acc;
+    for (int l = g->n_levels; l <= YCR_MAX_LEVELS; ++l) d.off[l] = acc;
+    return d;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Simple bump allocator over the caller's workspace.
+struct WsAlloc {
+    char* base;
+    size_t off;
+    size_t cap;
+    template <typename T>
+    T* take(size_t n) {
+        off = align_up(off, 256);
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

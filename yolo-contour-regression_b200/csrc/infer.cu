@@ -1,0 +1,348 @@
+// Inference path: Segment head polar decode (nn/modules/head.py:461-494, 559-570) and
+// non_max_suppression, polar variant (utils/ops.py:285-424) with the torchvision.ops.nms step
+// (utils/ops.py:407) as a sorted, chunked block-bitmask greedy suppression.
+// Paths under /root/reference/ultralytics-main/ultralytics/.
+#include "common.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// decode: one thread per (image, anchor); every access of a warp is a contiguous line along the
+// anchor dimension of the channel-major input (B, R+nc, HW_l) and output (B, 4+nc+3R, A).
+// Arithmetic mirrors the reference op by op (separate multiply and add, clamp after the stride
+// multiply) so boxes agree to the last bit wherever sin/cos tables do.
+// ------------------------------------------------------------------------------------------------
+struct DecodeArgs {
+    GridDev grid;
+    const float* feats[YCR_MAX_LEVELS];
+    int B, nc, R;
+    float cs[2 * 72];  // cos[0..R), sin[0..R)
+};
+
+__global__ void __launch_bounds__(256) k_decode(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
+    const int A = d.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.y;
+    const int an = blockIdx.x * 256 + threadIdx.x;
+    if (an >= A) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+        if (k < d.grid.n_levels && an >= d.grid.off[k]) l = k;
+    const int hw = d.grid.h[l] * d.grid.w[l];
+    const int al = an - d.grid.off[l];
+    const int iy = al / d.grid.w[l], ix = al - iy * d.grid.w[l];
+    const float stride = d.grid.stride[l];
+    const float ax = ((float)ix + 0.5f) * stride, ay = ((float)iy + 0.5f) * stride;
+    const int R = d.R, nc = d.nc;
+    const int CH = 4 + nc + 3 * R;
+    const float* f = d.feats[l] + (int64_t)b * (R + nc) * hw + al;
+    float* o = out + (int64_t)b * CH * A + an;
+    float minx = 3.4e38f, miny = 3.4e38f, maxx = -3.4e38f, maxy = -3.4e38f;
+#pragma unroll 4
+    for (int i = 0; i < R; ++i) {
+        const float dist = fmaxf(__fmul_rn(f[(int64_t)i * hw], stride), YCR_FLOOR);
+        const float x = __fadd_rn(__fmul_rn(dist, d.cs[i]), ax);
+        const float y = __fadd_rn(__fmul_rn(dist, d.cs[R + i]), ay);
+        minx = fminf(minx, x); maxx = fmaxf(maxx, x);
+        miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+        o[(int64_t)(4 + nc + i) * A] = x;
+        o[(int64_t)(4 + nc + R + i) * A] = y;
+        o[(int64_t)(4 + nc + 2 * R + i) * A] = (dist > 1.f) ? 1.f : 0.f;
+    }
+    o[0] = minx;
+    o[(int64_t)A] = miny;
+    o[(int64_t)2 * A] = maxx;
+    o[(int64_t)3 * A] = maxy;
+    const float* fc = f + (int64_t)R * hw;
+#pragma unroll 4
+    for (int c = 0; c < nc; ++c) {
+        const float x = fc[(int64_t)c * hw];
+        o[(int64_t)(4 + c) * A] = 1.f / (1.f + expf(-x));
+    }
+}
+
+int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, cudaStream_t st) {
+    DecodeArgs d{};
+    d.grid = make_grid_dev(grid);
+    for (int l = 0; l < grid->n_levels; ++l) d.feats[l] = feats[l];
+    d.B = B; d.nc = nc; d.R = R;
+    for (int i = 0; i < R; ++i) {
+        // angles = arange(0,360,360//R)/180.*pi in fp32 (nn/modules/head.py:466), then sin/cos
+        const float deg = (float)(i * (360 / R));
+        const float ang = (deg / 180.f) * (float)3.141592653589793;
+        d.cs[i] = (float)cos((double)ang);
+        d.cs[R + i] = (float)sin((double)ang);
+    }
+    const int A = d.grid.off[YCR_MAX_LEVELS];
+    dim3 g((A + 255) / 256, B);
+    k_decode<<<g, 256, 0, st>>>(d, allpred);
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NMS
+// ------------------------------------------------------------------------------------------------
+struct NmsWs {
+    unsigned long long* keys;  // [B][cap2]  (~score bits << 32) | (anchor*nc + class), sorted ascending
+    int* count;                // [B] candidates written (may exceed cap)
+    float4* boxes;             // [B][nsel_cap] class-offset boxes in sorted order
+    int cap, cap2, nsel_cap;
+};
+
+static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static size_t nms_ws_layout(NmsWs* ws, void* base, int B, int A, const ycr_nms_cfg_t* cfg) {
+    WsAlloc al{reinterpret_cast<char*>(base), 0, 0};
+    NmsWs w{};
+    const int nc = cfg->nc;
+    const bool multi = cfg->multi_label && nc > 1;
+    w.cap = multi ? A * nc : A;
+    w.cap2 = next_pow2(w.cap);
+    w.nsel_cap = (w.cap < cfg->max_nms) ? w.cap : cfg->max_nms;
+    w.keys = al.take<unsigned long long>((size_t)B * w.cap2);
+    w.count = al.take<int>(B + 1);
+    w.boxes = al.take<float4>((size_t)B * w.nsel_cap + 1);
+    if (ws) *ws = w;
+    return align_up(al.off, 256);
+}
+
+// conf filter + best-class / multi-label expansion (utils/ops.py:348, 380-391)
+__global__ void __launch_bounds__(256) k_nms_filter(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
+    const int b = blockIdx.y;
+    const int an = blockIdx.x * 256 + threadIdx.x;
+    if (an >= A) return;
+    const int nc = cfg.nc;
+    const bool multi = cfg.multi_label && nc > 1;
+    const float* p = pred + ((int64_t)b * CH + 4) * A + an;
+    float best = -3.4e38f;
+    int bc = 0, npass = 0;
+    for (int c = 0; c < nc; ++c) {
+        const float v = p[(int64_t)c * A];
+        if (v > best) { best = v; bc = c; }  // first maximum
+        npass += (v > cfg.conf_thres) ? 1 : 0;
+    }
+    if (!(best > cfg.conf_thres)) return;
+    unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
+    auto class_ok = [&](int c) {
+        if (!cfg.classes) return true;
+        for (int k = 0; k < cfg.n_classes; ++k)
+            if (cfg.classes[k] == c) return true;
+        return false;
+    };
+    if (!multi) {
+        if (!class_ok(bc)) return;
+        const int slot = atomicAdd(&ws.count[b], 1);
+        if (slot < ws.cap)
+            keys[slot] = ((unsigned long long)(~__float_as_uint(best)) << 32) | (unsigned)(an * nc + bc);
+    } else {
+        int slot = atomicAdd(&ws.count[b], npass);
+        for (int c = 0; c < nc; ++c) {
+            const float v = p[(int64_t)c * A];
+            if (v > cfg.conf_thres) {
+                // entries of filtered classes keep their slot but sort to the end and are cut off
+                const bool ok = class_ok(c);
+                if (slot < ws.cap)
+                    keys[slot] = ok ? (((unsigned long long)(~__float_as_uint(v)) << 32) | (unsigned)(an * nc + c))
+                                    : 0xFFFFFFFFFFFFFFFFull;
+                ++slot;
+            }
+        }
+    }
+}
+
+// block-wide bitonic sort of npow2 keys (shared or global memory)
+__device__ void bitonic_sort(unsigned long long* d, int npow2) {
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long x = d[i], y = d[ixj];
+                    const bool up = ((i & k) == 0);
+                    if ((x > y) == up) { d[i] = y; d[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+#define NMS_SORT_SMEM 4096
+
+// per image: sort candidates by (score desc, input order asc) = stable descending sort
+// (torchvision nms_kernel: scores.sort(0, descending=True)); cut to max_nms (utils/ops.py:401-402);
+// emit class-offset boxes `x[:, :4] + cls * max_wh` in fp32 (utils/ops.py:405-406).
+__global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
+    __shared__ unsigned long long s_keys[NMS_SORT_SMEM];
+    const int b = blockIdx.x;
+    unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
+    const int n = min(ws.count[b], ws.cap);
+    if (n == 0) return;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    if (np2 <= NMS_SORT_SMEM) {
+        for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = (i < n) ? keys[i] : 0xFFFFFFFFFFFFFFFFull;
+        __syncthreads();
+        bitonic_sort(s_keys, np2);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = s_keys[i];
+    } else {
+        for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0xFFFFFFFFFFFFFFFFull;
+        __syncthreads();
+        bitonic_sort(keys, np2);
+    }
+    __syncthreads();
+    const int nsel = min(n, ws.nsel_cap);
+    const int nc = cfg.nc;
+    float4* boxes = ws.boxes + (int64_t)b * ws.nsel_cap;
+    const float* p = pred + (int64_t)b * CH * A;
+    for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (k == 0xFFFFFFFFFFFFFFFFull) { boxes[i] = make_float4(0.f, 0.f, -1.f, -1.f); continue; }
+        const unsigned idx = (unsigned)(k & 0xFFFFFFFFull);
+        const int an = idx / nc, c = idx - an * nc;
+        const float off = cfg.agnostic ? 0.f : __fmul_rn((float)c, cfg.max_wh);
+        boxes[i] = make_float4(__fadd_rn(p[an], off), __fadd_rn(p[(int64_t)A + an], off),
+                               __fadd_rn(p[(int64_t)2 * A + an], off), __fadd_rn(p[(int64_t)3 * A + an], off));
+    }
+}
+
+__device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const float4 b, const float thr) {
+    // torchvision nms: inter / (area_a + area_b - inter) > thr, fp32, no epsilon
+    const float w = fmaxf(0.f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
+    const float h = fmaxf(0.f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
+    const float inter = __fmul_rn(w, h);
+    const float area_b = __fmul_rn(b.z - b.x, b.w - b.y);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return iou > thr;
+}
+
+#define NMS_NT 256
+#define NMS_MAX_SUPWORDS 1024  // 32768 boxes
+
+// per image greedy suppression in chunks of 64 sorted boxes: (A) 64x64 bitmask inside the chunk,
+// (B) one thread walks the chunk sequentially with bit operations, (C) the boxes kept in this
+// chunk suppress every later box in parallel.  Then the kept rows are gathered:
+// [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 408, 418).
+__global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
+                                                         float* __restrict__ out_rows, int* __restrict__ out_counts) {
+    __shared__ unsigned s_sup[NMS_MAX_SUPWORDS];
+    __shared__ unsigned long long s_mask[64];
+    __shared__ float4 s_box[64];
+    __shared__ float4 s_kbox[64];
+    __shared__ int s_kept[1024];
+    __shared__ int s_nk_chunk, s_nkept;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n = min(min(ws.count[b], ws.cap), ws.nsel_cap);
+    const int max_det = min(cfg.max_det, 1024);
+    const float4* boxes = ws.boxes + (int64_t)b * ws.nsel_cap;
+    const unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
+    // entries of filtered-out classes sorted to the end: drop them
+    int n_eff = n;
+    if (cfg.classes) {
+        __shared__ int s_cut;
+        if (tid == 0) s_cut = n;
+        __syncthreads();
+        for (int i = tid; i < n; i += NMS_NT)
+            if (keys[i] == 0xFFFFFFFFFFFFFFFFull) atomicMin(&s_cut, i);
+        __syncthreads();
+        n_eff = s_cut;
+    }
+    for (int i = tid; i < ((n_eff + 63) / 64) * 2 + 2 && i < NMS_MAX_SUPWORDS; i += NMS_NT) s_sup[i] = 0;
+    if (tid == 0) s_nkept = 0;
+    __syncthreads();
+    const float thr = cfg.iou_thres;
+    for (int c0 = 0; c0 < n_eff; c0 += 64) {
+        const int cn = min(64, n_eff - c0);
+        if (tid < 64) {
+            s_mask[tid] = 0ull;
+            if (tid < cn) s_box[tid] = boxes[c0 + tid];
+        }
+        __syncthreads();
+        {   // (A) thread -> row i, 16 columns
+            const int i = tid >> 2, q = tid & 3;
+            if (i < cn) {
+                const float4 bi = s_box[i];
+                const float ai = __fmul_rn(bi.z - bi.x, bi.w - bi.y);
+                unsigned long long m = 0ull;
+                for (int j = q * 16; j < q * 16 + 16; ++j)
+                    if (j > i && j < cn && iou_gt(bi, ai, s_box[j], thr)) m |= (1ull << j);
+                if (m) atomicOr(&s_mask[i], m);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {  // (B)
+            unsigned long long sup = (unsigned long long)s_sup[c0 >> 5] | ((unsigned long long)s_sup[(c0 >> 5) + 1] << 32);
+            int nk = 0, total = s_nkept;
+            for (int i = 0; i < cn && total < max_det; ++i) {
+                if (!((sup >> i) & 1ull)) {
+                    s_kbox[nk] = s_box[i];
+                    s_kept[total] = c0 + i;
+                    ++nk; ++total;
+                    sup |= s_mask[i];
+                }
+            }
+            s_nk_chunk = nk;
+            s_nkept = total;
+        }
+        __syncthreads();
+        if (s_nkept >= max_det) break;
+        const int nk = s_nk_chunk;
+        if (nk > 0) {  // (C)
+            for (int j = c0 + 64 + tid; j < n_eff; j += NMS_NT) {
+                if ((s_sup[j >> 5] >> (j & 31)) & 1u) continue;
+                const float4 bj = boxes[j];
+                const float aj = __fmul_rn(bj.z - bj.x, bj.w - bj.y);
+                bool dead = false;
+                for (int k = 0; k < nk && !dead; ++k) {
+                    const float4 bk = s_kbox[k];
+                    // same operand order as the reference loop: kept box i first
+                    const float ak = __fmul_rn(bk.z - bk.x, bk.w - bk.y);
+                    const float w = fmaxf(0.f, fminf(bk.z, bj.z) - fmaxf(bk.x, bj.x));
+                    const float h = fmaxf(0.f, fminf(bk.w, bj.w) - fmaxf(bk.y, bj.y));
+                    const float inter = __fmul_rn(w, h);
+                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, aj), inter));
+                    dead = iou > thr;
+                }
+                if (dead) atomicOr(&s_sup[j >> 5], 1u << (j & 31));
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    const int nk = s_nkept;
+    if (tid == 0) out_counts[b] = nk;
+    const int nc = cfg.nc, nm = CH - 4 - nc, W = 6 + nm;
+    const float* p = pred + (int64_t)b * CH * A;
+    float* o = out_rows + (int64_t)b * cfg.max_det * W;
+    for (int e = tid; e < nk * W; e += NMS_NT) {
+        const int r = e / W, col = e - r * W;
+        const unsigned long long k = keys[s_kept[r]];
+        const unsigned idx = (unsigned)(k & 0xFFFFFFFFull);
+        const int an = idx / nc, c = idx - an * nc;
+        float v;
+        if (col < 4) v = p[(int64_t)col * A + an];
+        else if (col == 4) v = __uint_as_float(~(unsigned)(k >> 32));
+        else if (col == 5) v = (float)c;
+        else v = p[(int64_t)(4 + nc + col - 6) * A + an];
+        o[(int64_t)r * W + col] = v;
+    }
+}
+
+size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_ws_layout(nullptr, nullptr, B, A, cfg); }
+
+int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
+               void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    NmsWs ws;
+    const size_t need = nms_ws_layout(&ws, workspace, B, A, cfg);
+    if (need > workspace_bytes) { ycr_set_error("nms workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
+    if (ws.nsel_cap > NMS_MAX_SUPWORDS * 32) { ycr_set_error("max_nms %d above supported %d", ws.nsel_cap, NMS_MAX_SUPWORDS * 32); return YCR_E_ARG; }
+    YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
+    dim3 g((A + 255) / 256, B);
+    k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws);
+    YCR_LAUNCH_CHECK();
+    k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws);
+    YCR_LAUNCH_CHECK();
+    k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts);
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}

@@ -1,0 +1,177 @@
+// Training path, streaming stage: BCE-with-logits class loss (utils/loss.py:866-867) against the
+// implicit sparse target_scores, the gradient of the whole loss with respect to every head output
+// written in the same pass, the final deterministic reductions, and GT packing
+// (utils/loss.py:215-239).  Paths under /root/reference/ultralytics-main/ultralytics/.
+#include "train_path.cuh"
+
+#define K5_NT 256
+
+// One thread per anchor, looping over the channel dimension: every global access of a warp is a
+// contiguous 128-byte line of the NCHW feature map (a_local is the fastest dimension).
+__global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                                       const float* f0, const float* f1, const float* f2, const float* f3,
+                                                       float* g0, float* g1, float* g2, float* g3, float cls_gain) {
+    __shared__ float s_red[K5_NT / 32];
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.y;
+    const int an = blockIdx.x * K5_NT + threadIdx.x;
+    const int R = a.cfg.rays, nc = a.cfg.num_classes;
+    float acc = 0.f;
+    if (an < A) {
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+            if (k < a.grid.n_levels && an >= a.grid.off[k]) l = k;
+        const float* f = (l == 0) ? f0 : (l == 1) ? f1 : (l == 2) ? f2 : f3;
+        float* g = (l == 0) ? g0 : (l == 1) ? g1 : (l == 2) ? g2 : g3;
+        const int hw = a.grid.h[l] * a.grid.w[l];
+        const int al = an - a.grid.off[l];
+        const int64_t base = (int64_t)b * (R + nc) * hw + al;
+        const int row = ws.pos_row[(int64_t)b * A + an];
+        int label = -1;
+        float tnorm = 0.f;
+        const float* pg = nullptr;
+        if (row >= 0) {
+            const int gi = ws.pos_g[(int64_t)b * ws.pos_cap + row];
+            int64_t lab = (int64_t)a.gt.labels[(int64_t)(b * a.gt.G + gi) * a.gt.labels_stride];
+            label = (int)(lab < 0 ? 0 : lab);
+            tnorm = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
+            pg = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
+        }
+        const float gscale = cls_gain * (float)a.gt.B / ws.tss[0];
+        if (g) {
+            if (pg) {
+                for (int i = 0; i < R; ++i) g[base + (int64_t)i * hw] = pg[i];
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < R; ++i) g[base + (int64_t)i * hw] = 0.f;
+            }
+        }
+        const float* fc = f + base + (int64_t)R * hw;
+        float* gc = g ? g + base + (int64_t)R * hw : nullptr;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+            const float x = fc[(int64_t)c * hw];
+            const float t = (c == label) ? tnorm : 0.f;
+            const float e = __expf(-fabsf(x));
+            acc += fmaxf(x, 0.f) - x * t + log1pf(e);
+            if (gc) {
+                const float r = __fdividef(1.f, 1.f + e);
+                const float sig = (x >= 0.f) ? r : e * r;
+                gc[(int64_t)c * hw] = (sig - t) * gscale;
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < K5_NT / 32) ? s_red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) ws.bce_part[blockIdx.y * gridDim.x + blockIdx.x] = v;
+    }
+}
+
+// total = (box_gain*l_box + cls_gain*l_cls) * B  (utils/loss.py:874-878); fixed-order reductions.
+__global__ void __launch_bounds__(256) k_loss_finalize(AssignWs ws, int B, int n_bce, float box_gain, float cls_gain,
+                                                       float* loss_out) {
+    __shared__ double s_b[256], s_p[256];
+    const int tid = threadIdx.x;
+    double sb = 0.0, sp = 0.0;
+    for (int i = tid; i < n_bce; i += 256) sb += (double)ws.bce_part[i];
+    for (int b = 0; b < B; ++b) {
+        const int n = ws.npos[b];
+        for (int r = tid; r < n; r += 256) sp += (double)ws.pos_loss[(int64_t)b * ws.pos_cap + r];
+    }
+    s_b[tid] = sb;
+    s_p[tid] = sp;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { s_b[tid] += s_b[tid + o]; s_p[tid] += s_p[tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double tss = (double)ws.tss[0];
+        const float l_box = (float)(s_p[0] / tss) * box_gain;
+        const float l_cls = (float)(s_b[0] / tss) * cls_gain;
+        loss_out[0] = (l_box + l_cls) * (float)B;
+        loss_out[1] = l_box;
+        loss_out[2] = l_cls;
+        loss_out[3] = (float)tss;
+    }
+}
+
+int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* const* feats, float* const* grads,
+                       const ycr_loss_cfg_t& lcfg, float* loss_out, cudaStream_t st) {
+    const int B = a.gt.B;
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    const float* f[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* g[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int l = 0; l < a.grid.n_levels; ++l) {
+        f[l] = feats[l];
+        g[l] = grads ? grads[l] : nullptr;
+    }
+    dim3 grid((A + K5_NT - 1) / K5_NT, B);
+    k_loss_stream<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain);
+    YCR_LAUNCH_CHECK();
+    k_loss_finalize<<<1, 256, 0, st>>>(ws, B, (int)(grid.x * grid.y), lcfg.box_gain, lcfg.cls_gain, loss_out);
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grad *= scale (device scalar); exits at once when the scalar is 1
+// ------------------------------------------------------------------------------------------------
+__global__ void k_scale(float* p, int64_t n, const float* scale) {
+    const float s = *scale;
+    if (s == 1.f) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] *= s;
+}
+
+int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st) {
+    if (n <= 0) return YCR_OK;
+    int blocks = (int)((n + 1023) / 1024);
+    if (blocks > YCR_NUM_SMS * 8) blocks = YCR_NUM_SMS * 8;
+    k_scale<<<blocks, 256, 0, st>>>(p, n, scale);
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GT packing: rows -> (B,G,725) padded, in px (utils/loss.py:215-239, 834-844).  Slot of row n inside
+// its image = number of earlier rows with the same image index (stable, as `targets[matches]`).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out) {
+    const int n = blockIdx.x;
+    const float* t = targets + (int64_t)n * rs;
+    const int b = (int)t[0];
+    __shared__ int s_slot;
+    if (threadIdx.x == 0) s_slot = 0;
+    __syncthreads();
+    int cnt = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) cnt += ((int)targets[(int64_t)k * rs] == b) ? 1 : 0;
+    if (cnt) atomicAdd(&s_slot, cnt);
+    __syncthreads();
+    const int slot = s_slot;
+    if (b < 0 || b >= B || slot >= G) return;
+    float* row = out + ((int64_t)b * G + slot) * (5 + 2 * YCR_C);
+    if (threadIdx.x == 0) {
+        row[0] = t[1];
+        const float cx = t[2] * img_w, cy = t[3] * img_h, w = t[4] * img_w, h = t[5] * img_h;
+        row[1] = cx - w / 2; row[2] = cy - h / 2; row[3] = cx + w / 2; row[4] = cy + h / 2;
+    }
+    // the reference scales the first 360 contour values by width and the last 360 by height although
+    // the data is x,y-interleaved (utils/loss.py:236-237); restated literally
+    for (int k = threadIdx.x; k < 2 * YCR_C; k += blockDim.x) row[5 + k] = t[6 + k] * ((k < YCR_C) ? img_w : img_h);
+}
+
+int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
+                        cudaStream_t st) {
+    YCR_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)B * G * (5 + 2 * YCR_C) * sizeof(float), st));
+    if (N > 0) {
+        k_pack_targets<<<N, 128, 0, st>>>(targets, rs, N, B, G, img_w, img_h, out);
+        YCR_LAUNCH_CHECK();
+    }
+    return YCR_OK;
+}

@@ -1,0 +1,161 @@
+"""Host-side mirror of `ultralytics/utils/loss.py` for the polar path (paths relative to
+/root/reference/ultralytics-main/ultralytics/): `v8SegmentationLoss` (utils/loss.py:772-878) and
+`MaskIOULoss` (utils/loss.py:109-127).  One C-ABI call runs assignment + polar targets + both loss
+terms + the gradient with respect to the head outputs."""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .tal import TaskAlignedAssigner, gt_struct
+
+
+class MaskIOULoss(nn.Module):
+    """utils/loss.py:109-127 — kept for API parity (`criterion.polar_loss`); the fused kernel computes
+    the same quantity for the positives without materialising them."""
+
+    def forward(self, pred_rays, target_rays, target_scores, target_scores_sum):
+        weight = target_scores.sum(-1)
+        total = torch.stack([pred_rays, target_rays], -1)
+        l_max = total.max(dim=2)[0]
+        l_min = total.min(dim=2)[0].clamp(min=1e-6)
+        loss = (l_max.sum(dim=1) / l_min.sum(dim=1)).log() * weight
+        return loss.sum() / target_scores_sum
+
+
+class _SegLossFn(torch.autograd.Function):
+    """loss = f(feat_0, feat_1, feat_2); forward already produced d loss / d feat_l."""
+
+    @staticmethod
+    def forward(ctx, crit, gt, cand_cap, *feats):
+        dev = feats[0].device
+        lib = L.lib()
+        B = feats[0].shape[0]
+        shapes = [tuple(f.shape[2:]) for f in feats]
+        cgrid = L.make_grid(shapes, crit.stride_list)
+        need_grad = any(f.requires_grad for f in feats)
+        grads = [torch.empty_like(f) for f in feats] if need_grad else None
+        loss_out = torch.empty(4, device=dev, dtype=torch.float32)
+        nbytes = lib.ycr_seg_loss_workspace_bytes(C.byref(cgrid), B, gt.G, C.byref(crit.acfg), cand_cap)
+        if nbytes == 0:
+            L.check(-1, "ycr_seg_loss_workspace_bytes")
+        ws = L.Workspace.get("seg_loss", nbytes, dev)
+        fp = L.ptr_array(feats)
+        gp = L.ptr_array(grads) if grads is not None else None
+        rc = lib.ycr_seg_loss_fwd_bwd(C.byref(cgrid), fp, gp, C.byref(gt), C.byref(crit.acfg), C.byref(crit.lcfg),
+                                      loss_out.data_ptr(), ws.data_ptr(), ws.numel(), cand_cap, L.stream_ptr(dev))
+        L.check(rc, "ycr_seg_loss_fwd_bwd")
+        ctx.grads = grads
+        ctx.cgrid = cgrid
+        ctx.channels = feats[0].shape[1]
+        ctx.B = B
+        ctx.mark_non_differentiable(loss_out)
+        return loss_out[0].clone(), loss_out
+
+    @staticmethod
+    def backward(ctx, g_total, _g_items):
+        grads = ctx.grads
+        if grads is None:
+            return (None, None, None) + (None,) * 3
+        dev = grads[0].device
+        g = g_total.detach().to(device=dev, dtype=torch.float32).contiguous()
+        rc = L.lib().ycr_scale_grads(C.byref(ctx.cgrid), ctx.B, ctx.channels, L.ptr_array(grads), g.data_ptr(),
+                                     L.stream_ptr(dev))
+        L.check(rc, "ycr_scale_grads")
+        return (None, None, None) + tuple(grads)
+
+
+class v8SegmentationLoss:
+    """utils/loss.py:772-878 (+ base v8DetectionLoss.__init__ utils/loss.py:192-214).
+
+    `__call__(preds, batch)` -> `(loss.sum() * batch_size  [with grad], loss.detach() (2,))`, where
+    loss = [box_gain * polar_iou_loss, cls_gain * bce] — identical to the reference's return."""
+
+    def __init__(self, model=None, *, nc=None, nm=36, strides=None, box=7.5, cls=0.5, device=None):
+        if model is not None:
+            device = next(model.parameters()).device
+            h = model.args
+            m = model.model[-1]
+            self.hyp = h
+            self.stride = m.stride
+            self.nc = m.nc
+            self.no = m.no
+            self.reg_max = getattr(m, "reg_max", 16)
+            self.nm = m.nm
+            self.overlap = getattr(h, "overlap_mask", True)
+            box, cls = float(h.box), float(h.cls)
+        else:
+            self.hyp = SimpleNamespace(box=box, cls=cls)
+            self.stride = torch.tensor(strides, dtype=torch.float32)
+            self.nc, self.nm = nc, nm
+            self.no = nc + nm
+            self.reg_max = 16
+            self.overlap = True
+        self.device = torch.device(device)
+        self.stride_list = [float(s) for s in (self.stride.tolist() if torch.is_tensor(self.stride) else self.stride)]
+        self.use_dfl = self.reg_max > 1
+        self.assigner = TaskAlignedAssigner(topk=10, num_classes=self.nc, alpha=0.5, beta=4.0)  # utils/loss.py:210
+        self.polar_loss = MaskIOULoss()
+        self.rays = 36 if self.nm == 36 else int(self.nm)  # utils/loss.py:818 keeps the first 36 channels
+        self.acfg = L.AssignCfg(10, int(self.nc), int(self.rays), 0.5, 4.0, 1e-9)
+        self.lcfg = L.LossCfg(float(box), float(cls))
+
+    # -- GT packing: utils/loss.py:834-844 + preprocess utils/loss.py:215-239 ----------------------
+    def pack_targets(self, batch, batch_size, img_hw):
+        """-> (packed (B,G,725) device tensor, candidate upper bound).  The rows are assembled on the host
+        (they arrive there from the dataloader), copied once, and padded/scaled by a kernel."""
+        dev = self.device
+        bi = batch["batch_idx"].view(-1).float()
+        N = bi.numel()
+        h, w = float(img_hw[0]), float(img_hw[1])
+        if N == 0:
+            return torch.zeros(batch_size, 0, 5 + 720, device=dev), 0
+        segs = batch["segments"]
+        seg = (torch.cat(list(segs)) if isinstance(segs, (list, tuple)) else segs).reshape(-1, 720).float()
+        cls = batch["cls"].reshape(-1).float()
+        bb = batch["bboxes"].reshape(-1, 4).float()
+        bi_h = bi.cpu()
+        G = int(torch.bincount(bi_h.long(), minlength=batch_size).max())
+        bb_h = bb.cpu()
+        xyxy = torch.stack([(bb_h[:, 0] - bb_h[:, 2] / 2) * w, (bb_h[:, 1] - bb_h[:, 3] / 2) * h,
+                            (bb_h[:, 0] + bb_h[:, 2] / 2) * w, (bb_h[:, 1] + bb_h[:, 3] / 2) * h], 1).contiguous()
+        cgrid = L.make_grid(self._shapes, self.stride_list)
+        cap = int(L.lib().ycr_candidate_bound_h(C.byref(cgrid), xyxy.data_ptr(), 4, N)) + 64
+        rows = torch.cat([bi.view(-1, 1).to(seg.device), cls.view(-1, 1).to(seg.device), bb.to(seg.device), seg], 1)
+        rows = rows.to(dev, non_blocking=True).contiguous()
+        out = torch.empty(batch_size, G, 5 + 720, device=dev)
+        rc = L.lib().ycr_pack_targets(rows.data_ptr(), rows.stride(0), N, batch_size, G, w, h, out.data_ptr(),
+                                      L.stream_ptr(dev))
+        L.check(rc, "ycr_pack_targets")
+        return out, cap
+
+    def __call__(self, preds, batch):
+        feats, _, _ = preds if len(preds) == 3 else preds[1]  # utils/loss.py:812
+        L.require_cuda(*feats)
+        feats = [f if (f.dtype == torch.float32 and f.is_contiguous()) else f.float().contiguous() for f in feats]
+        B = feats[0].shape[0]
+        if feats[0].shape[1] != self.rays + self.nc:
+            raise ValueError(f"head emits {feats[0].shape[1]} channels, expected rays+nc = {self.rays + self.nc}")
+        self._shapes = [tuple(f.shape[2:]) for f in feats]
+        img_hw = (feats[0].shape[2] * self.stride_list[0], feats[0].shape[3] * self.stride_list[0])
+        try:
+            packed, cap = self.pack_targets(batch, B, img_hw)
+        except RuntimeError as e:  # same re-wrap as utils/loss.py:850-856
+            raise TypeError("ERROR segment dataset incorrectly formatted or not a segment dataset.") from e
+        gt_labels, gt_boxes, gt_coor = packed.split((1, 4, 720), 2)
+        gt, keep = gt_struct(gt_labels, gt_boxes, gt_coor, None)
+        total, out = _SegLossFn.apply(self, gt, cap, *feats)
+        del keep
+        return total, out[1:3].detach()
+
+    def call_packed(self, feats, packed, cand_cap):
+        """Extension: same as __call__ with GTs already packed on the device ((B,G,725), px)."""
+        gt_labels, gt_boxes, gt_coor = packed.split((1, 4, 720), 2)
+        gt, keep = gt_struct(gt_labels, gt_boxes, gt_coor, None)
+        total, out = _SegLossFn.apply(self, gt, cand_cap, *feats)
+        del keep
+        return total, out[1:3].detach()

@@ -1,0 +1,66 @@
+"""Host-side mirror of `ultralytics/utils/ops.py::non_max_suppression` (polar variant,
+utils/ops.py:285-424; paths relative to /root/reference/ultralytics-main/ultralytics/)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def non_max_suppression(
+        prediction,
+        conf_thres=0.25,
+        iou_thres=0.45,
+        classes=None,
+        agnostic=False,
+        multi_label=False,
+        labels=(),
+        max_det=300,
+        nc=0,
+        max_time_img=0.05,
+        max_nms=30000,
+        max_wh=7680,
+):
+    """Same 12-argument signature, assertions and return type as utils/ops.py:285-298:
+    list (one per image) of (n_i, 6+nm) tensors [x1,y1,x2,y2,conf,cls,masks...] in descending score order.
+    Boxes are already xyxy (the polar variant does not convert).  One filter kernel, one per-image sort
+    kernel and one per-image suppression+gather kernel replace the per-image Python loop; the only host
+    synchronisation is the read of the B kept-counts that the list-of-tensors return type requires.
+    `max_time_img` is accepted and ignored (no wall-clock bail-out).  Apriori `labels` (save_hybrid
+    autolabelling, utils/ops.py:368-374) are not supported."""
+    assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
+    assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
+    if isinstance(prediction, (list, tuple)):
+        prediction = prediction[0]
+    if labels and any(len(lb) for lb in labels):
+        raise NotImplementedError("apriori labels (save_hybrid) are outside the B200 hot path")
+    L.require_cuda(prediction)
+    dev = prediction.device
+    pred = prediction if (prediction.dtype == torch.float32 and prediction.is_contiguous()) \
+        else prediction.float().contiguous()
+    B, CH, A = pred.shape
+    nc = nc or (CH - 4)
+    nm = CH - nc - 4
+    cfg = L.NmsCfg()
+    cfg.conf_thres, cfg.iou_thres = float(conf_thres), float(iou_thres)
+    cfg.agnostic, cfg.multi_label = int(bool(agnostic)), int(bool(multi_label) and nc > 1)
+    cfg.max_det, cfg.nc, cfg.max_nms, cfg.max_wh = int(max_det), int(nc), int(max_nms), float(max_wh)
+    cls_t = None
+    if classes is not None:
+        cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
+        cfg.classes, cfg.n_classes = cls_t.data_ptr(), cls_t.numel()
+    else:
+        cfg.classes, cfg.n_classes = None, 0
+    lib = L.lib()
+    nbytes = lib.ycr_nms_workspace_bytes(B, A, CH, C.byref(cfg))
+    ws = L.Workspace.get("nms", nbytes, dev)
+    rows = torch.empty(B, max_det, 6 + nm, device=dev, dtype=torch.float32)
+    counts = torch.empty(B, device=dev, dtype=torch.int32)
+    rc = lib.ycr_nms(pred.data_ptr(), B, CH, A, C.byref(cfg), rows.data_ptr(), counts.data_ptr(), ws.data_ptr(),
+                     ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "ycr_nms")
+    n = counts.tolist()
+    del cls_t
+    return [rows[i, :n[i]] for i in range(B)]
