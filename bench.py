@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the polar-contour hot path (BASELINE.json metric: assign+polar-loss images/sec @640).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+A "step" is one pass of v8SegmentationLoss (assignment + polar targets + loss, forward AND the gradient
+w.r.t. the head outputs) over one batch of synthetic head outputs and GTs.  Workload = BASELINE.json
+configs[1]: batch 64 @640, 20 GTs/img, 36 rays, nc=80 per GPU (weak scaling: every rank owns a full
+batch, as the reference's DDP does; the path has no data-path collective).
+
+  value   images/s with inputs resident in HBM, CUDA events, max over ranks
+  e2e     images/s through the public API with HOST inputs: pinned feature maps and the CPU batch dict
+          are copied H2D inside the timed region and the loss is read back D2H every step
+  roofline / kernels   per-kernel CUDA-event times from the library's own hooks, taken in the timed region
+  infer   decode + NMS images/s on config C3 (batch 256 @640, conf .25 / IoU .7), same method
+  cpu_baseline   the oracle port (torch-CPU restatement of the reference) on a bounded sample
+
+`--impl reference` times that CPU restatement alone on the host cores (the reference itself is Python
+under /root/reference and cannot travel to the GPU box)."""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, bounded sample
+# ------------------------------------------------------------------------------------------------
+def cpu_train_sample(cfg, n_images, repeats, seed=101):
+    from ycr_b200 import synth
+    from oracle import polar_oracle as po
+    sub = synth.PathConfig("cpu", n_images, cfg.gts, cfg.imgsz, rays=cfg.rays, nc=cfg.nc)
+    batch = synth.make_gts(sub, seed)
+    feats = synth.make_feats_near_gt(sub, seed, batch)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        po.seg_loss(feats, batch, sub.strides, sub.nc, sub.rays, with_grad=True)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from ycr_b200 import synth
+    cfg = synth.CONFIGS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_img = args.cpu_images
+    times = cpu_train_sample(cfg, n_img, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    ms = 1e3 * sum(timed) / len(timed)
+    val = n_img / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "assign+polar-loss images/sec @640", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: v8SegmentationLoss fwd+bwd, batch {cfg.batch} @{cfg.imgsz}, "
+                               f"{cfg.gts} GTs/img, {cfg.rays} rays, nc={cfg.nc}",
+                   "sample": f"{n_img} images per step (bounded sample of the batch)"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_img} images/step x {args.steps} steps, oracle/polar_oracle.seg_loss fwd+bwd"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import ycr_b200  # noqa: F401
+    from ycr_b200 import synth, _lib as L
+    from ycr_b200.loss import v8SegmentationLoss
+    from ycr_b200.head import decode
+    from ycr_b200.ops import non_max_suppression
+    lib = L.lib()
+    cfg = synth.CONFIGS[args.workload]
+    B, G, R, nc = cfg.batch, cfg.gts, cfg.rays, cfg.nc
+    A = cfg.anchors
+
+    # synthetic inputs (per rank: different seed, same shape)
+    seed = 1000 + rank
+    batch = synth.make_gts(cfg, seed)
+    gen_cfg = synth.PathConfig("gen", min(B, 16), G, cfg.imgsz, rays=R, nc=nc)
+    reps = (B + gen_cfg.batch - 1) // gen_cfg.batch
+    small = synth.make_feats(gen_cfg, seed)
+    feats_h = [torch.cat([f.roll(k, 0) for k in range(reps)], 0)[:B].contiguous().pin_memory() for f in small]
+    feats_d = [f.to(dev).requires_grad_(True) for f in feats_h]
+    crit = v8SegmentationLoss(nc=nc, nm=R, strides=cfg.strides, device=dev)
+    crit._shapes = [tuple(f.shape[2:]) for f in feats_d]
+    packed, cap = crit.pack_targets(batch, B, (cfg.imgsz, cfg.imgsz))
+    in_bytes = sum(f.numel() * 4 for f in feats_h)
+
+    def step_resident():
+        for f in feats_d:
+            f.grad = None
+        total, items = crit.call_packed(feats_d, packed, cap)
+        total.backward()
+        return total
+
+    def barrier():
+        if use_dist:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.check(lib.ycr_profile_begin(args.steps * 12 + 64), "ycr_profile_begin")
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    sums = (C.c_float * 16)()
+    counts = (C.c_int * 16)()
+    L.check(lib.ycr_profile_end(sums, counts), "ycr_profile_end")
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host inputs, H2D inside the timed region, loss read back ----
+    gt_rows_bytes = int(batch["batch_idx"].numel()) * 726 * 4
+
+    def step_e2e():
+        fd = [f.to(dev, non_blocking=True).requires_grad_(True) for f in feats_h]
+        total, items = crit((fd, 5, 2), batch)
+        total.backward()
+        return float(total)  # D2H read of the step's result
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e_steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    # ---- inference path (config C3), reported alongside ----
+    icfg = synth.CONFIGS["C3"]
+    ib = icfg.batch
+    ismall = synth.make_feats(synth.PathConfig("gi", 16, 0, icfg.imgsz, rays=R, nc=nc), seed + 1)
+    ifeats = [torch.cat([f.roll(k, 0) for k in range(ib // 16)], 0).contiguous().to(dev) for f in ismall]
+
+    def step_infer():
+        allpred = decode(ifeats, icfg.strides, nc, R)
+        return non_max_suppression(allpred, 0.25, 0.7, nc=nc, max_det=300)
+
+    for _ in range(3):
+        step_infer()
+    barrier()
+    L.check(lib.ycr_profile_begin(64), "ycr_profile_begin")
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i_steps = 5
+    i0.record()
+    for _ in range(i_steps):
+        dets = step_infer()
+    i1.record()
+    barrier()
+    ms_inf = i0.elapsed_time(i1)
+    isums = (C.c_float * 16)()
+    icounts = (C.c_int * 16)()
+    L.check(lib.ycr_profile_end(isums, icounts), "ycr_profile_end")
+    kept = sum(d.shape[0] for d in dets) / ib
+
+    # ---- reduce over ranks (max time) ----
+    t = torch.tensor([ms_total, ms_e2e, ms_inf], device=dev, dtype=torch.float64)
+    if use_dist:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e, ms_inf = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if use_dist:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step / 1e3)
+    e2e_val = world * B / (ms_e2e / e_steps / 1e3)
+    names = ["gt_setup", "cand_overlaps", "topk", "resolve", "positives", "loss_stream", "finalize", "decode",
+             "nms_filter", "nms_sort", "nms_suppress"]
+    kern = {names[i]: (sums[i] / counts[i]) for i in range(7) if counts[i]}
+    ikern = {names[i]: (isums[i] / icounts[i]) for i in range(7, 11) if icounts[i]}
+    dom = max(kern, key=kern.get)
+    bytes_img = 2 * 4 * A * (R + nc) + 4 * G * (5 + 720)            # SURVEY.md §8-d, per image
+    stream_bytes = 2 * 4 * A * (R + nc) * B                          # what loss_stream itself must move
+    path_gbs = bytes_img * B / (ms_step * 1e-3) / 1e9
+    dom_gbs = bytes_img * B / (kern[dom] * 1e-3) / 1e9
+    inf_bytes_img = 4 * A * (R + nc) + 4 * A * (4 + nc + 3 * R) + 4 * kept * (6 + 3 * R)
+    inf_val = world * ib / (ms_inf / i_steps / 1e3)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cpu_times = cpu_train_sample(cfg, args.cpu_images, 3) if world == 1 else None
+    cpu_val = (args.cpu_images / (sum(cpu_times[1:]) / len(cpu_times[1:]))) if cpu_times else None
+    line = {
+        "metric": "assign+polar-loss images/sec @640", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: v8SegmentationLoss fwd+bwd from head feats, batch {B}/GPU @{cfg.imgsz}, "
+                               f"{G} GTs/img, {R} rays, nc={nc}, A={A}",
+                   "l2": f"inputs per step {in_bytes / 1e6:.0f} MB + grads of the same size > 126 MB L2",
+                   "parallelism": f"dp{world}, no data-path collective"},
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "algorithmic bytes of the whole path (SURVEY 8-d: %.2f MB/img) / avg duration of the "
+                             "dominant kernel; see roofline_step and kernels_ms" % (bytes_img / 1e6)},
+        "roofline_step": {"achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
+                          "bytes_per_image": bytes_img},
+        "kernels_ms": kern,
+        "loss_stream_hbm_frac": (stream_bytes / (kern["loss_stream"] * 1e-3) / 1e9 / peak) if "loss_stream" in kern else None,
+        "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": in_bytes + gt_rows_bytes,
+                "d2h_bytes_per_step": 4, "steps": e_steps},
+        "gpu_launches": int(sum(counts[i] for i in range(7)) + 3 * args.steps),
+        "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
+                  "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",
+                  "ms_per_step": ms_inf / i_steps, "kernels_ms": ikern,
+                  "roofline_frac": inf_bytes_img * ib / (ms_inf / i_steps * 1e-3) / 1e9 / peak},
+        "clocks": clocks,
+    }
+    if cpu_val is not None:
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_images} images of the same workload, fwd+bwd, "
+                                          f"1 warm-up + 2 timed (oracle/polar_oracle.seg_loss)"}
+    print(json.dumps(line), flush=True)
+    if use_dist:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--cpu-images", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

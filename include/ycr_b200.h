@@ -101,6 +101,13 @@ typedef struct {
 const char* ycr_last_error(void);
 int ycr_version(void);
 
+/* Measurement hooks (bench.py): while enabled, every kernel of the path is bracketed by CUDA events on
+ * the launching stream.  ycr_profile_end waits for them and returns, per kernel tag (YCR_T_* order:
+ * 0 gt_setup, 1 cand_overlaps, 2 topk, 3 resolve, 4 positives, 5 loss_stream, 6 finalize, 7 decode,
+ * 8 nms_filter, 9 nms_sort, 10 nms_suppress), the summed milliseconds and launch count (16 entries). */
+int ycr_profile_begin(int max_records);
+int ycr_profile_end(float* ms_sum_h, int* count_h);
+
 /* ---- training path --------------------------------------------------------------------------- */
 
 /* Upper bound of in-box candidates (sum over GTs of anchors inside the GT box) computed on the host

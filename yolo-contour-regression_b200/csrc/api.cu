@@ -13,6 +13,26 @@ void ycr_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- per-kernel event timing --------------------------------------------------------------------
+#include <vector>
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_ev;       // pool
+static std::vector<int> g_prof_tag;              // tag of pair k (events 2k, 2k+1)
+static size_t g_prof_used = 0;
+
+void ycr_prof_mark(int tag, int end, cudaStream_t st) {
+    if (!g_prof_on) return;
+    if (!end) {
+        if (g_prof_used + 2 > g_prof_ev.size()) return;
+        g_prof_tag.push_back(tag);
+        cudaEventRecord(g_prof_ev[g_prof_used], st);
+    } else {
+        if (g_prof_tag.size() * 2 != g_prof_used + 2) return;
+        cudaEventRecord(g_prof_ev[g_prof_used + 1], st);
+        g_prof_used += 2;
+    }
+}
+
 int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st);
 int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
                         cudaStream_t st);
@@ -33,6 +53,36 @@ static int check_common(const ycr_grid_t* grid, const ycr_assign_cfg_t* cfg, int
 extern "C" {
 
 const char* ycr_last_error(void) { return g_err; }
+
+int ycr_profile_begin(int max_records) {
+    if (max_records < 1) { ycr_set_error("max_records must be positive"); return YCR_E_ARG; }
+    while ((int)g_prof_ev.size() < 2 * max_records) {
+        cudaEvent_t e;
+        YCR_CUDA_CHECK(cudaEventCreate(&e));
+        g_prof_ev.push_back(e);
+    }
+    g_prof_tag.clear();
+    g_prof_used = 0;
+    g_prof_on = true;
+    return YCR_OK;
+}
+
+int ycr_profile_end(float* ms_sum, int* count) {
+    g_prof_on = false;
+    if (!ms_sum || !count) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    for (int t = 0; t < YCR_T_COUNT; ++t) { ms_sum[t] = 0.f; count[t] = 0; }
+    const size_t pairs = g_prof_used / 2;
+    for (size_t k = 0; k < pairs; ++k) {
+        YCR_CUDA_CHECK(cudaEventSynchronize(g_prof_ev[2 * k + 1]));
+        float ms = 0.f;
+        YCR_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof_ev[2 * k], g_prof_ev[2 * k + 1]));
+        const int t = g_prof_tag[k];
+        if (t >= 0 && t < YCR_T_COUNT) { ms_sum[t] += ms; count[t] += 1; }
+    }
+    g_prof_tag.clear();
+    g_prof_used = 0;
+    return YCR_OK;
+}
 int ycr_version(void) { return 100; }
 
 int64_t ycr_candidate_bound_h(const ycr_grid_t* grid, const float* boxes_h, int64_t row_stride, int n_rows) {

@@ -595,7 +595,7 @@ static int launch_k1(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
     int dev = 0, sms = YCR_NUM_SMS;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    k_cand_overlaps<R, K1_NT><<<sms * per_sm, K1_NT, smem, st>>>(a, ws);
+    { YcrProfScope ps(YCR_T_CAND, st); k_cand_overlaps<R, K1_NT><<<sms * per_sm, K1_NT, smem, st>>>(a, ws); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -605,16 +605,16 @@ int launch_assign_core(const AssignArgs& a, const AssignWs& ws, cudaStream_t st)
     const int A = a.grid.off[YCR_MAX_LEVELS];
     YCR_CUDA_CHECK(cudaMemsetAsync(ws.err, 0, sizeof(int), st));
     if (BG > 0) {
-        k_gt_setup<<<1, 1024, 0, st>>>(a.grid, a.gt, ws, K1_NT);
+        { YcrProfScope ps(YCR_T_SETUP, st); k_gt_setup<<<1, 1024, 0, st>>>(a.grid, a.gt, ws, K1_NT); }
         YCR_LAUNCH_CHECK();
         int rc = (a.cfg.rays == 36) ? launch_k1<36>(a, ws, st) : launch_k1<72>(a, ws, st);
         if (rc) return rc;
-        k_topk_per_gt<<<(BG + 3) / 4, 128, 0, st>>>(a, ws);
+        { YcrProfScope ps(YCR_T_TOPK, st); k_topk_per_gt<<<(BG + 3) / 4, 128, 0, st>>>(a, ws); }
         YCR_LAUNCH_CHECK();
     }
     const size_t smem3 = (size_t)A * 4 + (size_t)ws.pos_cap * 12 + (size_t)G * 16 + 64;
     YCR_CUDA_CHECK(cudaFuncSetAttribute(k_resolve_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    k_resolve_image<<<B, K3_NT, smem3, st>>>(a, ws);
+    { YcrProfScope ps(YCR_T_RESOLVE, st); k_resolve_image<<<B, K3_NT, smem3, st>>>(a, ws); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -629,6 +629,7 @@ int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_d
     YCR_LAUNCH_CHECK();
     PosArgs pa{gt_dist, centerness, pos_capacity, img_base, tss, with_loss ? 1 : 0, lcfg ? lcfg->box_gain : 0.f};
     if (BG == 0) return YCR_OK;
+    YcrProfScope ps(YCR_T_POS, st);
     if (a.cfg.rays == 36) {
         const size_t smem = sizeof(PolarSmem<36, K1_NT>);
         YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

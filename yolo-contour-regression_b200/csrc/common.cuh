@@ -13,6 +13,17 @@
 
 void ycr_set_error(const char* fmt, ...);
 
+// Optional per-kernel CUDA-event timing (ycr_profile_begin/read in the C ABI); a no-op unless enabled.
+enum { YCR_T_SETUP = 0, YCR_T_CAND = 1, YCR_T_TOPK = 2, YCR_T_RESOLVE = 3, YCR_T_POS = 4, YCR_T_STREAM = 5,
+       YCR_T_FINAL = 6, YCR_T_DECODE = 7, YCR_T_NMS_FILTER = 8, YCR_T_NMS_SORT = 9, YCR_T_NMS_SUPPRESS = 10,
+       YCR_T_COUNT = 16 };
+void ycr_prof_mark(int tag, int end, cudaStream_t st);
+struct YcrProfScope {
+    int tag; cudaStream_t st;
+    YcrProfScope(int t, cudaStream_t s) : tag(t), st(s) { ycr_prof_mark(tag, 0, st); }
+    ~YcrProfScope() { ycr_prof_mark(tag, 1, st); }
+};
+
 #define YCR_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

@@ -74,7 +74,7 @@ int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int 
     }
     const int A = d.grid.off[YCR_MAX_LEVELS];
     dim3 g((A + 255) / 256, B);
-    k_decode<<<g, 256, 0, st>>>(d, allpred);
+    { YcrProfScope ps(YCR_T_DECODE, st); k_decode<<<g, 256, 0, st>>>(d, allpred); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -338,11 +338,11 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
     if (ws.nsel_cap > NMS_MAX_SUPWORDS * 32) { ycr_set_error("max_nms %d above supported %d", ws.nsel_cap, NMS_MAX_SUPWORDS * 32); return YCR_E_ARG; }
     YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
     dim3 g((A + 255) / 256, B);
-    k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws);
+    { YcrProfScope ps(YCR_T_NMS_FILTER, st); k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws); }
     YCR_LAUNCH_CHECK();
-    k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws);
+    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws); }
     YCR_LAUNCH_CHECK();
-    k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts);
+    { YcrProfScope ps(YCR_T_NMS_SUPPRESS, st); k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }

@@ -112,9 +112,9 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* con
         g[l] = grads ? grads[l] : nullptr;
     }
     dim3 grid((A + K5_NT - 1) / K5_NT, B);
-    k_loss_stream<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain);
+    { YcrProfScope ps(YCR_T_STREAM, st); k_loss_stream<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain); }
     YCR_LAUNCH_CHECK();
-    k_loss_finalize<<<1, 256, 0, st>>>(ws, B, (int)(grid.x * grid.y), lcfg.box_gain, lcfg.cls_gain, loss_out);
+    { YcrProfScope ps(YCR_T_FINAL, st); k_loss_finalize<<<1, 256, 0, st>>>(ws, B, (int)(grid.x * grid.y), lcfg.box_gain, lcfg.cls_gain, loss_out); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
