@@ -210,6 +210,16 @@ def run_ours(args):
     L.check(lib.ycr_profile_end(sums, counts), "ycr_profile_end")
     clocks = sampler.stop() if rank == 0 else None
 
+    if args.quick:
+        names = ["gt_setup", "cand_overlaps", "topk", "resolve", "positives", "loss_stream", "finalize"]
+        if rank == 0:
+            st = (C.c_ulonglong * 4)()
+            lib.ycr_debug_stats(st, 1)
+            print(json.dumps({"quick": True, "ms_per_step": ms_total / args.steps,
+                              "stats_per_candidate": {"candidates": st[0], "queued_pairs": st[1] / max(st[0], 1),
+                                                      "scan_pairs": st[2] / max(st[0], 1)},
+                              "kernels_ms": {names[i]: sums[i] / counts[i] for i in range(7) if counts[i]}}), flush=True)
+        return
     # ---- e2e: host inputs, H2D inside the timed region, loss read back ----
     gt_rows_bytes = int(batch["batch_idx"].numel()) * 726 * 4
 
@@ -217,7 +227,7 @@ def run_ours(args):
         fd = [f.to(dev, non_blocking=True).requires_grad_(True) for f in feats_h]
         total, items = crit((fd, 5, 2), batch)
         total.backward()
-        return float(total)  # D2H read of the step's result
+        return float(total.detach())  # D2H read of the step's result
 
     for _ in range(3):
         step_e2e()
@@ -332,6 +342,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--cpu-images", type=int, default=4)
+    ap.add_argument("--quick", action="store_true", help="resident train-path timing only (for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

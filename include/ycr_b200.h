@@ -107,6 +107,10 @@ int ycr_version(void);
  * 8 nms_filter, 9 nms_sort, 10 nms_suppress), the summed milliseconds and launch count (16 entries). */
 int ycr_profile_begin(int max_records);
 int ycr_profile_end(float* ms_sum_h, int* count_h);
+/* Work counters of the candidate kernel since the last reset (synchronises the device):
+ * out_h[0] candidates swept, [1] (candidate,ray) pairs the own angular bin could not settle,
+ * [2] pairs that needed the exact 360-point scan, [3] reserved. */
+int ycr_debug_stats(unsigned long long* out_h, int reset);
 
 /* ---- training path --------------------------------------------------------------------------- */
 

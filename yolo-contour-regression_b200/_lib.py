@@ -63,6 +63,7 @@ EXPORTS = {
     "ycr_version": (C.c_int, []),
     "ycr_profile_begin": (C.c_int, [C.c_int]),
     "ycr_profile_end": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ycr_debug_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "ycr_candidate_bound_h": (C.c_int64, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int]),
     "ycr_assign_workspace_bytes": (C.c_size_t, [C.POINTER(Grid), C.c_int, C.c_int, C.POINTER(AssignCfg), C.c_int64]),
     "ycr_assign": (C.c_int, [C.POINTER(Grid), C.POINTER(PredView), C.POINTER(Gt), C.POINTER(AssignCfg),

@@ -33,6 +33,7 @@ void ycr_prof_mark(int tag, int end, cudaStream_t st) {
     }
 }
 
+int debug_stats(unsigned long long* out_h, int reset);
 int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st);
 int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
                         cudaStream_t st);
@@ -65,6 +66,11 @@ int ycr_profile_begin(int max_records) {
     g_prof_used = 0;
     g_prof_on = true;
     return YCR_OK;
+}
+
+int ycr_debug_stats(unsigned long long* out_h, int reset) {
+    if (!out_h) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    return debug_stats(out_h, reset);
 }
 
 int ycr_profile_end(float* ms_sum, int* count) {

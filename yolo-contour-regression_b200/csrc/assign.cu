@@ -10,6 +10,20 @@
 #define K1_NT 64
 #define K3_NT 512
 
+// running totals since the last ycr_debug_stats(reset): candidates, pairs queued for neighbourhood
+// settlement, pairs that needed the exact scan (measurement aid, three atomics per block iteration)
+__device__ unsigned long long g_ycr_stats[4];
+
+int debug_stats(unsigned long long* out_h, int reset) {
+    YCR_CUDA_CHECK(cudaDeviceSynchronize());
+    YCR_CUDA_CHECK(cudaMemcpyFromSymbol(out_h, g_ycr_stats, sizeof(unsigned long long) * 4));
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        YCR_CUDA_CHECK(cudaMemcpyToSymbol(g_ycr_stats, z, sizeof(z)));
+    }
+    return YCR_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
             cur_bg = bg;
         }
-        if (tid == 0) sm.qcount = 0;
+        if (tid == 0) { sm.qcount = 0; sm.q2count = 0; }
         __syncthreads();
         const int c = (work - ws.chunk_off[bg]) * NT + tid;
         const bool active = c < ws.ncand[bg];
@@ -195,6 +209,11 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
         __syncthreads();
         polar_settle_queue<R, NT>(sm, a.pc, tid);
         __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&g_ycr_stats[0], (unsigned long long)min(NT, ws.ncand[bg] - (work - ws.chunk_off[bg]) * NT));
+            atomicAdd(&g_ycr_stats[1], (unsigned long long)sm.qcount);
+            atomicAdd(&g_ycr_stats[2], (unsigned long long)sm.q2count);
+        }
         if (active) {
             const int b = bg / a.gt.G;
             const int l = ap.level;
@@ -441,7 +460,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
     const int base = pa.img_base[b];
     for (int r0 = 0; r0 < cnt; r0 += NT) {
         __syncthreads();
-        if (tid == 0) sm.qcount = 0;
+        if (tid == 0) { sm.qcount = 0; sm.q2count = 0; }
         __syncthreads();
         const int r = r0 + tid;
         const bool active = r < cnt;

@@ -7,20 +7,22 @@
 //   * a point belongs to the bin of its nearest ray (|delta| <= 180/R deg, decided by a cross/dot
 //     test against the current ray direction - no atan2 anywhere);
 //   * the bin's four nearest points live in registers as packed (23-bit fixed-point |sin delta|,
-//     9-bit point index) keys and are kept sorted with 8 integer min/max per point; they are
+//     9-bit point index) keys kept sorted with 7 independent integer min/max per point; they are
 //     spilled to / refilled from a per-thread shared-memory slot only when the sweep enters another
-//     bin, and every bin change is logged as a (bin, first point) segment record;
+//     bin, where the exact number of points of the bin left behind is accumulated as well;
 //   * after the sweep a ray is settled when its own bin certifies the answer (four points strictly
-//     inside the bin, or nothing within 3 degrees); the few others (sparse side of the contour) are
-//     queued block-wide and settled exactly by widening the window bin by bin over the segment
-//     records, with a pseudo-angle key that is monotone over [0,180] degrees.
+//     inside the bin, or nothing within 3 degrees).  The others (sparse side of the contour) are
+//     queued block-wide; a queued pair is settled by evaluating the contour neighbourhoods of the
+//     points its bin did catch, and the result is certified against the per-bin counts (every point of
+//     the bins that could hold a nearer point has been looked at).  What cannot be certified goes to
+//     a second queue that one warp per pair settles by an exact scan of all 360 points.
 // Every path is exact with respect to the reference whenever the reference's own selection is not
 // within ~1e-5 degrees of a tie (the parity tests' margin checker uses 2e-4 degrees).
 #pragma once
 #include "common.cuh"
 
-#define YCR_SEGCAP 64
-#define YCR_NSCHED 5
+#define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
+#define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
 
 struct PolarConst {
     float tan_in;       // tan(hw + 0.01 deg): bin membership |crs| <= tan_in * dot
@@ -28,10 +30,11 @@ struct PolarConst {
     uint32_t q_res;     // fixed(sin(hw - 0.02 deg)): 4th key below this => top-4 certified
     uint32_t q_gate;    // fixed(sin(3 deg))
     int gate_l1;        // 1 when hw - 0.01 > 3: an own bin without a point <= 3 deg certifies the gate
-    int sched[YCR_NSCHED];      // window growth in bins
-    float pk_win[YCR_NSCHED];   // pseudo-angle of ((2m+1)*hw - 0.02 deg)
-    int gate_ok[YCR_NSCHED];    // (2m+1)*hw - 0.02 > 3
-    float pk_gate;              // pseudo-angle of 3 deg
+    int empty3_gate;    // 1 when 3*hw - 0.03 > 3: three empty bins certify the gate
+    int nwin;           // R/2 + 1 windows: window m covers bins ray-m .. ray+m
+    float pk_lo[YCR_MAXWIN];  // pseudo-angle of ((2m+1)*hw - 0.03 deg)
+    float pk_hi[YCR_MAXWIN];  // pseudo-angle of ((2m+1)*hw + 0.03 deg)
+    float pk_gate;            // pseudo-angle of 3 deg
 };
 
 template <int R, int NT>
@@ -40,19 +43,19 @@ struct PolarSmem {
     float2 contour[YCR_C];
     float2 raydir[R];                  // (cos, sin) of i*360/R deg
     float2 anchor[NT];
-    unsigned short seg[YCR_SEGCAP][NT];
-    unsigned short nseg[NT];
-    unsigned short queue[NT * R];      // (thread << 7) | ray
-    int qcount;
-    int work;                          // broadcast slot for the persistent loop
+    unsigned char cnt[R][NT];          // points per bin (saturating at 255)
+    unsigned short queue[NT * R];      // (thread << 7) | ray : pairs the own bin could not settle
+    unsigned short queue2[NT * R];     // pairs that need the exact scan
+    int qcount, q2count;
 };
 
+// sorted insert with depth-2 dependency: new k_i = max(k_{i-1}, min(k_i, x))
 __device__ __forceinline__ void insert4(uint32_t& k0, uint32_t& k1, uint32_t& k2, uint32_t& k3, uint32_t x) {
-    uint32_t lo;
-    lo = min(k0, x); x = max(k0, x); k0 = lo;
-    lo = min(k1, x); x = max(k1, x); k1 = lo;
-    lo = min(k2, x); x = max(k2, x); k2 = lo;
-    k3 = min(k3, x);
+    const uint32_t n3 = max(k2, min(k3, x));
+    const uint32_t n2 = max(k1, min(k2, x));
+    const uint32_t n1 = max(k0, min(k1, x));
+    k0 = min(k0, x);
+    k1 = n1; k2 = n2; k3 = n3;
 }
 
 // Monotone map of the angle between v and the ray onto [0,4], from q=|cross| and d=dot.
@@ -62,48 +65,70 @@ __device__ __forceinline__ float pseudo_angle(float q, float d) {
     return 4.f + q / d;
 }
 
+// float sorted insert of (k, v) into four slots
+__device__ __forceinline__ void finsert4(float (&fk)[4], float (&fv)[4], float k, float v) {
+    if (k < fk[3]) {
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+            if (k < fk[s]) { float t = fk[s]; fk[s] = k; k = t; t = fv[s]; fv[s] = v; v = t; }
+        if (k < fk[3]) { fk[3] = k; fv[3] = v; }
+    }
+}
+
 // One sweep over the contour for the anchor (ax, ay) of this thread.
 template <int R, int NT>
 __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, float ax, float ay) {
 #pragma unroll 4
-    for (int i = 0; i < R; ++i) sm.list[i][tid] = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
-    int ray = 0;
+    for (int i = 0; i < R; ++i) {
+        sm.list[i][tid] = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
+        sm.cnt[i][tid] = 0;
+    }
+    int ray = 0, run = 0;
     float cr = 1.f, sr = 0.f;
     uint32_t k0 = YCR_EMPTY, k1 = YCR_EMPTY, k2 = YCR_EMPTY, k3 = YCR_EMPTY;
-    int nseg = 1;
-    sm.seg[0][tid] = 0;  // (bin 0, first point 0)
     const float tan_in = pc.tan_in, ks = pc.key_scale;
-#pragma unroll 4
-    for (int j = 0; j < YCR_C; ++j) {
-        const float2 p = sm.contour[j];
-        float vx = p.x - ax, vy = p.y - ay;
-        float l2 = fmaf(vx, vx, vy * vy);
-        if (l2 == 0.f) { vx = 1.f; l2 = 1.f; }  // atan2(0,0) = 0: direction of ray 0
-        const float inv = rsqrtf(l2);
-        float dot = fmaf(vx, cr, vy * sr);
-        float crs = fmaf(vy, cr, -vx * sr);
-        if (!(fabsf(crs) <= tan_in * dot)) {
-            sm.list[ray][tid] = make_uint4(k0, k1, k2, k3);
-            int guard = 0;
-            do {
-                ray += (crs >= 0.f) ? 1 : -1;
-                ray = (ray < 0) ? ray + R : ((ray >= R) ? ray - R : ray);
-                const float2 cs = sm.raydir[ray];
-                cr = cs.x; sr = cs.y;
-                dot = fmaf(vx, cr, vy * sr);
-                crs = fmaf(vy, cr, -vx * sr);
-            } while (!(fabsf(crs) <= tan_in * dot) && ++guard < R);
-            const uint4 L = sm.list[ray][tid];
-            k0 = L.x; k1 = L.y; k2 = L.z; k3 = L.w;
-            if (nseg < YCR_SEGCAP) sm.seg[nseg][tid] = (unsigned short)(ray | (j << 7));
-            ++nseg;
+    for (int j0 = 0; j0 < YCR_C; j0 += 4) {
+        // phase 1: everything that does not depend on the current bin, four points at once
+        float vx[4], vy[4], inv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 p = sm.contour[j0 + u];
+            vx[u] = p.x - ax;
+            vy[u] = p.y - ay;
+            float l2 = fmaf(vx[u], vx[u], vy[u] * vy[u]);
+            if (l2 == 0.f) { vx[u] = 1.f; l2 = 1.f; }  // atan2(0,0) = 0: direction of ray 0
+            inv[u] = rsqrtf(l2);
         }
-        const float key = fabsf(crs) * inv;
-        const uint32_t pk = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)j;
-        insert4(k0, k1, k2, k3, pk);
+        // phase 2: bin tracking and insertion, in contour order
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float dot = fmaf(vx[u], cr, vy[u] * sr);
+            float crs = fmaf(vy[u], cr, -vx[u] * sr);
+            if (!(fabsf(crs) <= tan_in * dot)) {
+                sm.list[ray][tid] = make_uint4(k0, k1, k2, k3);
+                sm.cnt[ray][tid] = (unsigned char)min(255, (int)sm.cnt[ray][tid] + run);
+                run = 0;
+                const int dir = (crs >= 0.f) ? 1 : -1;
+                int guard = 0;
+                do {
+                    ray += dir;
+                    ray = (ray < 0) ? ray + R : ((ray >= R) ? ray - R : ray);
+                    const float2 cs = sm.raydir[ray];
+                    cr = cs.x; sr = cs.y;
+                    dot = fmaf(vx[u], cr, vy[u] * sr);
+                    crs = fmaf(vy[u], cr, -vx[u] * sr);
+                } while (!(fabsf(crs) <= tan_in * dot) && ++guard < R);
+                const uint4 L = sm.list[ray][tid];
+                k0 = L.x; k1 = L.y; k2 = L.z; k3 = L.w;
+            }
+            ++run;
+            const float key = fabsf(crs) * inv[u];
+            const uint32_t pk = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
+            insert4(k0, k1, k2, k3, pk);
+        }
     }
     sm.list[ray][tid] = make_uint4(k0, k1, k2, k3);
-    sm.nseg[tid] = (unsigned short)min(nseg, 65535);
+    sm.cnt[ray][tid] = (unsigned char)min(255, (int)sm.cnt[ray][tid] + run);
     sm.anchor[tid] = make_float2(ax, ay);
 }
 
@@ -148,77 +173,188 @@ __device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const Pol
     }
 }
 
-// Exact settlement of one queued (owner thread, ray) pair by window growth over segment records.
+// Neighbourhood settlement of one queued (owner thread, ray) pair.  Returns false when the result
+// cannot be certified (the pair then takes the exact scan).
+//   A. evaluate the contour neighbourhoods (+-YCR_NBR indices) of the seed points (what the own bin
+//      caught); this gives a first 4th-nearest angle and the window (in bins) that must be known;
+//   B. grow every evaluated index range at both ends while the end points still lie inside that
+//      window (along a locally monotone contour this visits exactly the points of the window);
+//   C. certify: the number of evaluated points inside the (final, possibly smaller) window equals the
+//      number of points the sweep counted in the window's bins.
+#define YCR_EVCAP 48
 template <int R, int NT>
-__device__ __noinline__ float polar_settle_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray) {
+__device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
+                                                  float& result) {
     const float2 a = sm.anchor[owner];
     const float2 cs = sm.raydir[ray];
-    float fk0 = 1e30f, fk1 = 1e30f, fk2 = 1e30f, fk3 = 1e30f;
-    float fd0 = 0.f, fd1 = 0.f, fd2 = 0.f, fd3 = 0.f;  // squared distances ride along
-    auto eval = [&](int j) {
+    int seed[4];
+    int ns = 0;
+    {
+        const uint4 L = sm.list[ray][owner];
+        if (L.x != YCR_EMPTY) {
+            seed[ns++] = L.x & 511u;
+            if (L.y != YCR_EMPTY) seed[ns++] = L.y & 511u;
+            if (L.z != YCR_EMPTY) seed[ns++] = L.z & 511u;
+            if (L.w != YCR_EMPTY) seed[ns++] = L.w & 511u;
+        } else {  // empty own bin (only reachable when hw < 3 deg): nearest two of each neighbour bin
+            const uint4 A = sm.list[(ray + R - 1) % R][owner];
+            const uint4 B = sm.list[(ray + 1) % R][owner];
+            if (A.x != YCR_EMPTY) seed[ns++] = A.x & 511u;
+            if (A.y != YCR_EMPTY) seed[ns++] = A.y & 511u;
+            if (B.x != YCR_EMPTY) seed[ns++] = B.x & 511u;
+            if (B.y != YCR_EMPTY) seed[ns++] = B.y & 511u;
+            if (ns == 0) {
+                if (!pc.empty3_gate) return false;
+                result = YCR_FLOOR;  // three empty bins: nothing within 3*hw - 0.01 > 3 degrees
+                return true;
+            }
+        }
+    }
+    // rotate point indices so that the first seed sits mid-range and ranges do not wrap
+    const int origin = (seed[0] + YCR_C / 2) % YCR_C;
+    for (int s = 0; s < ns; ++s) seed[s] = (seed[s] - origin + YCR_C) % YCR_C;
+    for (int s = 1; s < ns; ++s)  // insertion sort, ns <= 4
+        for (int t = s; t > 0 && seed[t] < seed[t - 1]; --t) { const int x = seed[t]; seed[t] = seed[t - 1]; seed[t - 1] = x; }
+    if (seed[0] < YCR_NBR || seed[ns - 1] >= YCR_C - YCR_NBR) return false;
+    float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
+    float ev[YCR_EVCAP];
+    int ne = 0;
+    auto eval = [&](int jr) -> float {
+        int j = jr + origin;
+        j = (j >= YCR_C) ? j - YCR_C : j;
         const float2 p = sm.contour[j];
-        float vx = p.x - a.x, vy = p.y - a.y;
+        float vx = p.x - a.x;
+        const float vy = p.y - a.y;
         const float l2 = fmaf(vx, vx, vy * vy);
         if (l2 == 0.f) vx = 1.f;
         const float d = fmaf(vx, cs.x, vy * cs.y);
         const float q = fabsf(fmaf(vy, cs.x, -vx * cs.y));
-        float k = pseudo_angle(q, d), v = l2;
-        // sorted insert of (k, v)
-        if (k < fk3) {
-            if (k < fk0) { float t = fk0; fk0 = k; k = t; t = fd0; fd0 = v; v = t; }
-            if (k < fk1) { float t = fk1; fk1 = k; k = t; t = fd1; fd1 = v; v = t; }
-            if (k < fk2) { float t = fk2; fk2 = k; k = t; t = fd2; fd2 = v; v = t; }
-            if (k < fk3) { fk3 = k; fd3 = v; }
-        }
+        const float k = pseudo_angle(q, d);
+        ev[ne++] = k;
+        finsert4(fk, fd, k, l2);
+        return k;
     };
-    const int nrec = sm.nseg[owner];
-    if (nrec > YCR_SEGCAP) {
-        for (int j = 0; j < YCR_C; ++j) eval(j);  // record overflow: plain exact scan
-    } else {
-        const uint4 L = sm.list[ray][owner];
-        if (L.x != YCR_EMPTY) eval(L.x & 511u);
-        if (L.y != YCR_EMPTY) eval(L.y & 511u);
-        if (L.z != YCR_EMPTY) eval(L.z & 511u);
-        if (L.w != YCR_EMPTY) eval(L.w & 511u);
-        int mprev = 0;
-        for (int s = 0; s < YCR_NSCHED; ++s) {
-            const int m = pc.sched[s];
-            for (int k = 0; k < nrec; ++k) {
-                const unsigned rec = sm.seg[k][owner];
-                int db = abs((int)(rec & 127u) - ray);
-                db = min(db, R - db);
-                if (db > mprev && db <= m) {
-                    const int st = rec >> 7;
-                    const int en = (k + 1 < nrec) ? (sm.seg[k + 1][owner] >> 7) : YCR_C;
-                    for (int j = st; j < en; ++j) eval(j);
-                }
-            }
-            mprev = m;
-            if (2 * m + 1 >= R) break;                       // the whole circle is covered
-            if (fk3 < pc.pk_win[s]) break;                   // four points certified inside the window
-            if (pc.gate_ok[s] && fk0 > pc.pk_gate) break;    // nothing within 3 degrees, certified
+    // A: merged seed neighbourhoods -> disjoint ranges [rlo, rhi]
+    int rlo[4], rhi[4];
+    int nr = 0;
+    for (int s = 0; s < ns; ++s) {
+        const int lo = seed[s] - YCR_NBR, hi = seed[s] + YCR_NBR;
+        if (nr > 0 && lo <= rhi[nr - 1] + 1) {
+            for (int jr = rhi[nr - 1] + 1; jr <= hi; ++jr) eval(jr);
+            rhi[nr - 1] = max(rhi[nr - 1], hi);
+        } else {
+            for (int jr = lo; jr <= hi; ++jr) eval(jr);
+            rlo[nr] = lo; rhi[nr] = hi; ++nr;
         }
     }
-    if (fk0 > pc.pk_gate) return YCR_FLOOR;
-    const float m2 = fmaxf(fmaxf(fd0, fd1), fmaxf(fd2, fd3));
-    return fmaxf(sqrtf(m2), YCR_FLOOR);
+    // window that must be fully known, from the first estimate of the threshold
+    float thr = (fk[0] > pc.pk_gate) ? pc.pk_gate : fk[3];
+    int m = 0;
+    while (m < pc.nwin && !(pc.pk_lo[m] > thr)) ++m;
+    if (m >= pc.nwin - 1) return false;
+    // B: grow the ranges while their end points are still inside the window
+    const float win_hi = pc.pk_hi[m];
+    for (int r = 0; r < nr; ++r) {
+        const int lo_limit = (r > 0) ? rhi[r - 1] + 1 : 0;
+        while (rlo[r] > lo_limit && ne < YCR_EVCAP) {
+            --rlo[r];
+            if (eval(rlo[r]) >= win_hi) break;
+        }
+        const int hi_limit = (r + 1 < nr) ? rlo[r + 1] - 1 : YCR_C - 1;
+        while (rhi[r] < hi_limit && ne < YCR_EVCAP) {
+            ++rhi[r];
+            if (eval(rhi[r]) >= win_hi) break;
+        }
+    }
+    if (ne >= YCR_EVCAP) return false;
+    // C: certify against the bin counts, with the final threshold (never wider than the first)
+    const bool gated = fk[0] > pc.pk_gate;
+    thr = gated ? pc.pk_gate : fk[3];
+    m = 0;
+    while (!(pc.pk_lo[m] > thr)) ++m;
+    int nbins = sm.cnt[ray][owner];
+    bool sat = nbins == 255;
+    for (int db = 1; db <= m; ++db) {
+        const int c1 = sm.cnt[(ray + db) % R][owner], c2 = sm.cnt[(ray + R - db) % R][owner];
+        sat |= (c1 == 255) | (c2 == 255);
+        nbins += c1 + c2;
+    }
+    if (sat) return false;
+    int n_in = 0, n_maybe = 0;
+    const float lo = pc.pk_lo[m], hi = pc.pk_hi[m];
+    for (int e = 0; e < ne; ++e) {
+        n_in += (ev[e] < lo) ? 1 : 0;
+        n_maybe += (ev[e] < hi) ? 1 : 0;
+    }
+    if (n_in != n_maybe || n_in != nbins) return false;
+    result = gated ? YCR_FLOOR : fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
+    return true;
 }
 
-// Block-wide: settle all queued pairs densely (any thread may serve any owner).
+// Exact scan of all points for one pair, one warp per pair (lanes stride the contour).
+template <int R, int NT>
+__device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
+                                                 unsigned lane) {
+    const float2 a = sm.anchor[owner];
+    const float2 cs = sm.raydir[ray];
+    float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane; j < YCR_C; j += 32) {
+        const float2 p = sm.contour[j];
+        float vx = p.x - a.x;
+        const float vy = p.y - a.y;
+        const float l2 = fmaf(vx, vx, vy * vy);
+        if (l2 == 0.f) vx = 1.f;
+        const float d = fmaf(vx, cs.x, vy * cs.y);
+        const float q = fabsf(fmaf(vy, cs.x, -vx * cs.y));
+        finsert4(fk, fd, pseudo_angle(q, d), l2);
+    }
+    float first = 0.f, maxd = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float m = fk[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const unsigned who = __ballot_sync(0xffffffffu, fk[0] == m);
+        const int src = __ffs(who) - 1;
+        const float dsel = __shfl_sync(0xffffffffu, fd[0], src);
+        if ((int)lane == src) {
+            fk[0] = fk[1]; fk[1] = fk[2]; fk[2] = fk[3]; fk[3] = 1e30f;
+            fd[0] = fd[1]; fd[1] = fd[2]; fd[2] = fd[3];
+        }
+        if (r == 0) first = m;
+        maxd = fmaxf(maxd, dsel);
+    }
+    if (first > pc.pk_gate) return YCR_FLOOR;
+    return fmaxf(sqrtf(maxd), YCR_FLOOR);
+}
+
+// Block-wide: settle all queued pairs (any thread may serve any owner), then the exact-scan queue.
+// Must be called by all NT threads; contains block barriers.
 template <int R, int NT>
 __device__ __forceinline__ void polar_settle_queue(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid) {
     const int nq = sm.qcount;
     for (int q = tid; q < nq; q += NT) {
         const unsigned e = sm.queue[q];
         const int owner = e >> 7, ray = e & 127u;
-        const float t = polar_settle_pair<R, NT>(sm, pc, owner, ray);
-        sm.list[ray][owner].x = __float_as_uint(t);
+        float t;
+        if (polar_settle_pair<R, NT>(sm, pc, owner, ray, t)) sm.list[ray][owner].x = __float_as_uint(t);
+        else sm.queue2[atomicAdd(&sm.q2count, 1)] = (unsigned short)e;
+    }
+    __syncthreads();
+    const int n2 = sm.q2count;
+    const unsigned lane = tid & 31u;
+    for (int q = tid >> 5; q < n2; q += NT / 32) {
+        const unsigned e = sm.queue2[q];
+        const int owner = e >> 7, ray = e & 127u;
+        const float t = polar_scan_pair<R, NT>(sm, pc, owner, ray, lane);
+        if (lane == 0) sm.list[ray][owner].x = __float_as_uint(t);
     }
 }
 
 static inline double ycr_deg2rad(double d) { return d * 3.14159265358979323846 / 180.0; }
 
 static inline double ycr_pseudo_host(double deg) {
+    if (deg > 179.99) deg = 179.99;
     const double q = sin(ycr_deg2rad(deg)), d = cos(ycr_deg2rad(deg));
     if (d >= q) return q / d;
     if (d > -q) return 2.0 - d / q;
@@ -235,14 +371,16 @@ static inline PolarConst make_polar_const(int R) {
     pc.q_gate = (uint32_t)(sin(ycr_deg2rad(YCR_GATE_DEG)) * scale);
     if (YCR_GATE_DEG >= hw + 0.01) pc.q_gate = 0x7FFFFFu;  // every in-bin key is below the gate
     pc.gate_l1 = (hw - 0.01 > YCR_GATE_DEG) ? 1 : 0;
-    const int sched[YCR_NSCHED] = {1, 2, 4, 8, R / 2};
-    for (int s = 0; s < YCR_NSCHED; ++s) {
-        pc.sched[s] = sched[s];
-        double win = (2 * sched[s] + 1) * hw - 0.02;
-        if (win > 179.9) win = 179.9;
-        pc.pk_win[s] = (float)ycr_pseudo_host(win);
-        pc.gate_ok[s] = (win > YCR_GATE_DEG) ? 1 : 0;
+    pc.empty3_gate = (3 * hw - 0.03 > YCR_GATE_DEG) ? 1 : 0;
+    pc.nwin = R / 2 + 1;
+    for (int m = 0; m < YCR_MAXWIN; ++m) {
+        const double w = (2 * m + 1) * hw;
+        pc.pk_lo[m] = (float)ycr_pseudo_host(w - 0.03);
+        pc.pk_hi[m] = (float)ycr_pseudo_host(w + 0.03);
     }
+    // the last window is the whole circle: nothing lies outside it
+    pc.pk_lo[R / 2] = 5.f;
+    pc.pk_hi[R / 2] = 5.f;
     pc.pk_gate = (float)ycr_pseudo_host(YCR_GATE_DEG);
     return pc;
 }
