@@ -75,7 +75,9 @@ __device__ __forceinline__ void finsert4(float (&fk)[4], float (&fv)[4], float k
     }
 }
 
-// One sweep over the contour for the anchor (ax, ay) of this thread.
+// One sweep over the contour for the anchor (ax, ay) of this thread.  The per-ray lists stay in
+// shared memory and every point does a uniform read-insert-write on the list of its bin, so the
+// only divergent code is the (rare, two-instruction-deep) step to a neighbouring bin.
 template <int R, int NT>
 __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, float ax, float ay) {
 #pragma unroll 4
@@ -83,9 +85,8 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
         sm.list[i][tid] = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
         sm.cnt[i][tid] = 0;
     }
-    int ray = 0, run = 0;
+    int ray = 0;
     float cr = 1.f, sr = 0.f;
-    uint32_t k0 = YCR_EMPTY, k1 = YCR_EMPTY, k2 = YCR_EMPTY, k3 = YCR_EMPTY;
     const float tan_in = pc.tan_in, ks = pc.key_scale;
     for (int j0 = 0; j0 < YCR_C; j0 += 4) {
         // phase 1: everything that does not depend on the current bin, four points at once
@@ -105,9 +106,6 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             float dot = fmaf(vx[u], cr, vy[u] * sr);
             float crs = fmaf(vy[u], cr, -vx[u] * sr);
             if (!(fabsf(crs) <= tan_in * dot)) {
-                sm.list[ray][tid] = make_uint4(k0, k1, k2, k3);
-                sm.cnt[ray][tid] = (unsigned char)min(255, (int)sm.cnt[ray][tid] + run);
-                run = 0;
                 const int dir = (crs >= 0.f) ? 1 : -1;
                 int guard = 0;
                 do {
@@ -118,19 +116,19 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
                     dot = fmaf(vx[u], cr, vy[u] * sr);
                     crs = fmaf(vy[u], cr, -vx[u] * sr);
                 } while (!(fabsf(crs) <= tan_in * dot) && ++guard < R);
-                const uint4 L = sm.list[ray][tid];
-                k0 = L.x; k1 = L.y; k2 = L.z; k3 = L.w;
             }
-            ++run;
             const float key = fabsf(crs) * inv[u];
             const uint32_t pk = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
-            insert4(k0, k1, k2, k3, pk);
+            uint4 L = sm.list[ray][tid];
+            insert4(L.x, L.y, L.z, L.w, pk);
+            sm.list[ray][tid] = L;
+            const unsigned c = sm.cnt[ray][tid];
+            sm.cnt[ray][tid] = (unsigned char)min(255u, c + 1u);
         }
     }
-    sm.list[ray][tid] = make_uint4(k0, k1, k2, k3);
-    sm.cnt[ray][tid] = (unsigned char)min(255, (int)sm.cnt[ray][tid] + run);
     sm.anchor[tid] = make_float2(ax, ay);
 }
+
 
 template <int R, int NT>
 __device__ __forceinline__ float dist2_of(const PolarSmem<R, NT>& sm, uint32_t packed, float ax, float ay) {
