@@ -100,7 +100,9 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             if (l2 == 0.f) { vx[u] = 1.f; l2 = 1.f; }  // atan2(0,0) = 0: direction of ray 0
             inv[u] = rsqrtf(l2);
         }
-        // phase 2: bin tracking and insertion, in contour order
+        // phase 2: bin of each of the four points (serial only through the tracked ray) and its key
+        int rb[4];
+        uint32_t pk[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float dot = fmaf(vx[u], cr, vy[u] * sr);
@@ -117,13 +119,33 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
                     crs = fmaf(vy[u], cr, -vx[u] * sr);
                 } while (!(fabsf(crs) <= tan_in * dot) && ++guard < R);
             }
+            rb[u] = ray;
             const float key = fabsf(crs) * inv[u];
-            const uint32_t pk = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
-            uint4 L = sm.list[ray][tid];
-            insert4(L.x, L.y, L.z, L.w, pk);
-            sm.list[ray][tid] = L;
-            const unsigned c = sm.cnt[ray][tid];
-            sm.cnt[ray][tid] = (unsigned char)min(255u, c + 1u);
+            pk[u] = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
+        }
+        // phase 3: the four lists and counts are fetched together ...
+        uint4 L[4];
+        unsigned c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            L[u] = sm.list[rb[u]][tid];
+            c[u] = sm.cnt[rb[u]][tid];
+        }
+        // phase 4: ... updated in contour order, forwarding the result of an earlier point of the same
+        // bin (the usual case) instead of going through shared memory again ...
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int w = 0; w < u; ++w)
+                if (rb[w] == rb[u]) { L[u] = L[w]; c[u] = c[w]; }
+            insert4(L[u].x, L[u].y, L[u].z, L[u].w, pk[u]);
+            c[u] = min(255u, c[u] + 1u);
+        }
+        // phase 5: ... and written back in order (a later store to the same bin carries all updates)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            sm.list[rb[u]][tid] = L[u];
+            sm.cnt[rb[u]][tid] = (unsigned char)c[u];
         }
     }
     sm.anchor[tid] = make_float2(ax, ay);
