@@ -26,6 +26,7 @@
 
 struct PolarConst {
     float tan_in;       // tan(hw + 0.01 deg): bin membership |crs| <= tan_in * dot
+    float cos_step, sin_step;  // cos/sin of the ray spacing 360/R deg
     float key_scale;    // fixed-point scale of |sin delta| so that in-bin keys fit 23 bits
     uint32_t q_res;     // fixed(sin(hw - 0.02 deg)): 4th key below this => top-4 certified
     uint32_t q_gate;    // fixed(sin(3 deg))
@@ -44,8 +45,8 @@ struct PolarSmem {
     float2 raydir[R];                  // (cos, sin) of i*360/R deg
     float2 anchor[NT];
     unsigned char cnt[R][NT];          // points per bin (saturating at 255)
-    unsigned short queue[NT * R];      // (thread << 7) | ray : pairs the own bin could not settle
-    unsigned short queue2[NT * R];     // pairs that need the exact scan
+    unsigned short queue[NT * R / 2];  // (thread << 7) | ray : pairs the own bin could not settle;
+                                       // bit 15 is set later on pairs that need the exact scan
     int qcount, q2count;
 };
 
@@ -60,9 +61,10 @@ __device__ __forceinline__ void insert4(uint32_t& k0, uint32_t& k1, uint32_t& k2
 
 // Monotone map of the angle between v and the ray onto [0,4], from q=|cross| and d=dot.
 __device__ __forceinline__ float pseudo_angle(float q, float d) {
-    if (d >= q) return (d > 0.f) ? q / d : 0.f;
-    if (d > -q) return 2.f - d / q;
-    return 4.f + q / d;
+    // (approximate division: 2 ulp on a key whose decisive gaps are margin-checked at >= 1e-4 deg)
+    if (d >= q) return (d > 0.f) ? __fdividef(q, d) : 0.f;
+    if (d > -q) return 2.f - __fdividef(d, q);
+    return 4.f + __fdividef(q, d);
 }
 
 // float sorted insert of (k, v) into four slots
@@ -100,15 +102,32 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             if (l2 == 0.f) { vx[u] = 1.f; l2 = 1.f; }  // atan2(0,0) = 0: direction of ray 0
             inv[u] = rsqrtf(l2);
         }
-        // phase 2: bin of each of the four points (serial only through the tracked ray) and its key
+        // phase 2: bin of each of the four points (serial only through the tracked ray) and its key.
+        // The usual move - one bin up or down - is branch-free: cross/dot and the ray direction are
+        // rotated by one ray spacing in registers; the exact direction is reloaded from the table at
+        // the start of every group, so at most four rotations (a few 1e-6 deg) ever accumulate.
         int rb[4];
         uint32_t pk[4];
+        {
+            const float2 cs = sm.raydir[ray];
+            cr = cs.x; sr = cs.y;
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             float dot = fmaf(vx[u], cr, vy[u] * sr);
             float crs = fmaf(vy[u], cr, -vx[u] * sr);
-            if (!(fabsf(crs) <= tan_in * dot)) {
-                const int dir = (crs >= 0.f) ? 1 : -1;
+            const bool need = !(fabsf(crs) <= tan_in * dot);
+            const bool up = crs >= 0.f;
+            const float sg = up ? pc.sin_step : -pc.sin_step;
+            const float dot2 = fmaf(dot, pc.cos_step, crs * sg);
+            const float crs2 = fmaf(crs, pc.cos_step, -dot * sg);
+            const float cr2 = fmaf(cr, pc.cos_step, -sr * sg);
+            const float sr2 = fmaf(sr, pc.cos_step, cr * sg);
+            int ray2 = ray + (up ? 1 : -1);
+            ray2 = (ray2 < 0) ? ray2 + R : ((ray2 >= R) ? ray2 - R : ray2);
+            if (need) { ray = ray2; dot = dot2; crs = crs2; cr = cr2; sr = sr2; }
+            if (!(fabsf(crs) <= tan_in * dot)) {  // more than one bin away (sparse side / jump): walk, exactly
+                const int dir = up ? 1 : -1;
                 int guard = 0;
                 do {
                     ray += dir;
@@ -159,6 +178,28 @@ __device__ __forceinline__ float dist2_of(const PolarSmem<R, NT>& sm, uint32_t p
     return fmaf(vx, vx, vy * vy);
 }
 
+template <int R, int NT>
+__device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
+                                                  float& result);
+
+// Exact scan of all points by one thread (only used when the block queue overflows).
+template <int R, int NT>
+__device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray) {
+    const float2 a = sm.anchor[owner];
+    const float2 cs = sm.raydir[ray];
+    float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < YCR_C; ++j) {
+        const float2 p = sm.contour[j];
+        float vx = p.x - a.x;
+        const float vy = p.y - a.y;
+        const float l2 = fmaf(vx, vx, vy * vy);
+        if (l2 == 0.f) vx = 1.f;
+        finsert4(fk, fd, pseudo_angle(fabsf(fmaf(vy, cs.x, -vx * cs.y)), fmaf(vx, cs.x, vy * cs.y)), l2);
+    }
+    if (fk[0] > pc.pk_gate) return YCR_FLOOR;
+    return fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
+}
+
 // Own-bin settlement of every ray of this thread; unsettled rays go to the block queue.
 // On return sm.list[i][tid].x holds the float bits of the target for settled rays.
 template <int R, int NT>
@@ -188,7 +229,16 @@ __device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const Pol
             int base = 0;
             if (lane == 0) base = atomicAdd(&sm.qcount, __popc(ball));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (unsettled) sm.queue[base + __popc(ball & ((1u << lane) - 1u))] = (unsigned short)((tid << 7) | i);
+            if (unsettled) {
+                const int slot = base + __popc(ball & ((1u << lane) - 1u));
+                if (slot < NT * R / 2) {
+                    sm.queue[slot] = (unsigned short)((tid << 7) | i);
+                } else {  // queue full (pathological block): settle right here, serially
+                    float t;
+                    if (!polar_settle_pair<R, NT>(sm, pc, tid, i, t)) t = polar_scan_serial<R, NT>(sm, pc, tid, i);
+                    sm.list[i][tid].x = __float_as_uint(t);
+                }
+            }
         }
     }
 }
@@ -352,20 +402,23 @@ __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, con
 // Must be called by all NT threads; contains block barriers.
 template <int R, int NT>
 __device__ __forceinline__ void polar_settle_queue(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid) {
-    const int nq = sm.qcount;
+    const int nq = min(sm.qcount, NT * R / 2);
+    int nfail = 0;
     for (int q = tid; q < nq; q += NT) {
         const unsigned e = sm.queue[q];
         const int owner = e >> 7, ray = e & 127u;
         float t;
         if (polar_settle_pair<R, NT>(sm, pc, owner, ray, t)) sm.list[ray][owner].x = __float_as_uint(t);
-        else sm.queue2[atomicAdd(&sm.q2count, 1)] = (unsigned short)e;
+        else { sm.queue[q] = (unsigned short)(e | 0x8000u); ++nfail; }
     }
+    if (nfail) atomicAdd(&sm.q2count, nfail);
     __syncthreads();
-    const int n2 = sm.q2count;
+    if (sm.q2count == 0) return;
     const unsigned lane = tid & 31u;
-    for (int q = tid >> 5; q < n2; q += NT / 32) {
-        const unsigned e = sm.queue2[q];
-        const int owner = e >> 7, ray = e & 127u;
+    for (int q = tid >> 5; q < nq; q += NT / 32) {
+        const unsigned e = sm.queue[q];
+        if (!(e & 0x8000u)) continue;  // warp-uniform: every lane reads the same entry
+        const int owner = (e & 0x7FFFu) >> 7, ray = e & 127u;
         const float t = polar_scan_pair<R, NT>(sm, pc, owner, ray, lane);
         if (lane == 0) sm.list[ray][owner].x = __float_as_uint(t);
     }
@@ -385,6 +438,8 @@ static inline PolarConst make_polar_const(int R) {
     PolarConst pc{};
     const double hw = 180.0 / R;
     pc.tan_in = (float)tan(ycr_deg2rad(hw + 0.01));
+    pc.cos_step = (float)cos(ycr_deg2rad(2 * hw));
+    pc.sin_step = (float)sin(ycr_deg2rad(2 * hw));
     const double scale = 8388607.0 / sin(ycr_deg2rad(hw + 0.02));
     pc.key_scale = (float)scale;
     pc.q_res = (uint32_t)(sin(ycr_deg2rad(hw - 0.02)) * scale);
