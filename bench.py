@@ -190,6 +190,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.quick_infer:
+        icfg = synth.CONFIGS["C3"]
+        ismall = synth.make_feats(synth.PathConfig("gi", 16, 0, icfg.imgsz, rays=R, nc=nc), seed + 1)
+        ifeats = [torch.cat([f.roll(k, 0) for k in range(icfg.batch // 16)], 0).contiguous().to(dev) for f in ismall]
+        L.check(lib.ycr_profile_begin(256), "ycr_profile_begin")
+        for _ in range(args.warmup + args.steps):
+            non_max_suppression(decode(ifeats, icfg.strides, nc, R), 0.25, 0.7, nc=nc, max_det=300)
+        torch.cuda.synchronize()
+        sums = (C.c_float * 16)()
+        counts = (C.c_int * 16)()
+        L.check(lib.ycr_profile_end(sums, counts), "ycr_profile_end")
+        names = {7: "decode", 8: "nms_filter", 9: "nms_sort", 10: "nms_suppress"}
+        print(json.dumps({"quick_infer": True, "kernels_ms": {n: sums[i] / counts[i] for i, n in names.items()}}))
+        return
     for _ in range(max(args.warmup, 3)):
         step_resident()
     barrier()
@@ -343,6 +357,7 @@ def main():
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--cpu-images", type=int, default=4)
     ap.add_argument("--quick", action="store_true", help="resident train-path timing only (for ncu runs)")
+    ap.add_argument("--quick-infer", action="store_true", help="decode+NMS kernels only (for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,6 +9,7 @@
 
 #define K1_NT 64
 #define K3_NT 512
+#define K4_NT 32   // positives per GT are ~topk: one warp per block
 
 // running totals since the last ycr_debug_stats(reset): candidates, pairs queued for neighbourhood
 // settlement, pairs that needed the exact scan (measurement aid, three atomics per block iteration)
@@ -650,13 +651,13 @@ int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_d
     if (BG == 0) return YCR_OK;
     YcrProfScope ps(YCR_T_POS, st);
     if (a.cfg.rays == 36) {
-        const size_t smem = sizeof(PolarSmem<36, K1_NT>);
-        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_positive_targets<36, K1_NT><<<BG, K1_NT, smem, st>>>(a, ws, pa);
+        const size_t smem = sizeof(PolarSmem<36, K4_NT>);
+        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_positive_targets<36, K4_NT><<<BG, K4_NT, smem, st>>>(a, ws, pa);
     } else {
-        const size_t smem = sizeof(PolarSmem<72, K1_NT>);
-        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<72, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_positive_targets<72, K1_NT><<<BG, K1_NT, smem, st>>>(a, ws, pa);
+        const size_t smem = sizeof(PolarSmem<72, K4_NT>);
+        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<72, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_positive_targets<72, K4_NT><<<BG, K4_NT, smem, st>>>(a, ws, pa);
     }
     YCR_LAUNCH_CHECK();
     return YCR_OK;

@@ -60,6 +60,66 @@ __global__ void __launch_bounds__(256) k_decode(const __grid_constant__ DecodeAr
     }
 }
 
+// Vectorised variant: one thread per four consecutive anchors of a row (W_l and H_l*W_l multiples of 4),
+// 128-bit loads/stores.
+__global__ void __launch_bounds__(256) k_decode_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
+    const int A = d.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.y;
+    const int an = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (an >= A) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+        if (k < d.grid.n_levels && an >= d.grid.off[k]) l = k;
+    const int hw = d.grid.h[l] * d.grid.w[l];
+    const int al = an - d.grid.off[l];
+    const int iy = al / d.grid.w[l], ix = al - iy * d.grid.w[l];
+    const float stride = d.grid.stride[l];
+    const float ay = ((float)iy + 0.5f) * stride;
+    const float ax0 = ((float)ix + 0.5f) * stride, ax1 = ((float)(ix + 1) + 0.5f) * stride;
+    const float ax2 = ((float)(ix + 2) + 0.5f) * stride, ax3 = ((float)(ix + 3) + 0.5f) * stride;
+    const int R = d.R, nc = d.nc;
+    const int CH = 4 + nc + 3 * R;
+    const float* f = d.feats[l] + (int64_t)b * (R + nc) * hw + al;
+    float* o = out + (int64_t)b * CH * A + an;
+    float4 minx = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f), miny = minx;
+    float4 maxx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), maxy = maxx;
+#pragma unroll 4
+    for (int i = 0; i < R; ++i) {
+        const float4 r = __ldcs(reinterpret_cast<const float4*>(f + (int64_t)i * hw));
+        const float c = d.cs[i], s = d.cs[R + i];
+        float4 dist, x, y, v;
+        dist.x = fmaxf(__fmul_rn(r.x, stride), YCR_FLOOR); dist.y = fmaxf(__fmul_rn(r.y, stride), YCR_FLOOR);
+        dist.z = fmaxf(__fmul_rn(r.z, stride), YCR_FLOOR); dist.w = fmaxf(__fmul_rn(r.w, stride), YCR_FLOOR);
+        x.x = __fadd_rn(__fmul_rn(dist.x, c), ax0); x.y = __fadd_rn(__fmul_rn(dist.y, c), ax1);
+        x.z = __fadd_rn(__fmul_rn(dist.z, c), ax2); x.w = __fadd_rn(__fmul_rn(dist.w, c), ax3);
+        y.x = __fadd_rn(__fmul_rn(dist.x, s), ay); y.y = __fadd_rn(__fmul_rn(dist.y, s), ay);
+        y.z = __fadd_rn(__fmul_rn(dist.z, s), ay); y.w = __fadd_rn(__fmul_rn(dist.w, s), ay);
+        v.x = (dist.x > 1.f) ? 1.f : 0.f; v.y = (dist.y > 1.f) ? 1.f : 0.f;
+        v.z = (dist.z > 1.f) ? 1.f : 0.f; v.w = (dist.w > 1.f) ? 1.f : 0.f;
+        minx.x = fminf(minx.x, x.x); minx.y = fminf(minx.y, x.y); minx.z = fminf(minx.z, x.z); minx.w = fminf(minx.w, x.w);
+        maxx.x = fmaxf(maxx.x, x.x); maxx.y = fmaxf(maxx.y, x.y); maxx.z = fmaxf(maxx.z, x.z); maxx.w = fmaxf(maxx.w, x.w);
+        miny.x = fminf(miny.x, y.x); miny.y = fminf(miny.y, y.y); miny.z = fminf(miny.z, y.z); miny.w = fminf(miny.w, y.w);
+        maxy.x = fmaxf(maxy.x, y.x); maxy.y = fmaxf(maxy.y, y.y); maxy.z = fmaxf(maxy.z, y.z); maxy.w = fmaxf(maxy.w, y.w);
+        __stcs(reinterpret_cast<float4*>(o + (int64_t)(4 + nc + i) * A), x);
+        __stcs(reinterpret_cast<float4*>(o + (int64_t)(4 + nc + R + i) * A), y);
+        __stcs(reinterpret_cast<float4*>(o + (int64_t)(4 + nc + 2 * R + i) * A), v);
+    }
+    *reinterpret_cast<float4*>(o) = minx;
+    *reinterpret_cast<float4*>(o + (int64_t)A) = miny;
+    *reinterpret_cast<float4*>(o + (int64_t)2 * A) = maxx;
+    *reinterpret_cast<float4*>(o + (int64_t)3 * A) = maxy;
+    const float* fc = f + (int64_t)R * hw;
+#pragma unroll 4
+    for (int c = 0; c < nc; ++c) {
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(fc + (int64_t)c * hw));
+        float4 p;
+        p.x = 1.f / (1.f + expf(-x.x)); p.y = 1.f / (1.f + expf(-x.y));
+        p.z = 1.f / (1.f + expf(-x.z)); p.w = 1.f / (1.f + expf(-x.w));
+        *reinterpret_cast<float4*>(o + (int64_t)(4 + c) * A) = p;   // class rows are re-read by NMS: keep in L2
+    }
+}
+
 int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, cudaStream_t st) {
     DecodeArgs d{};
     d.grid = make_grid_dev(grid);
@@ -73,8 +133,18 @@ int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int 
         d.cs[R + i] = (float)sin((double)ang);
     }
     const int A = d.grid.off[YCR_MAX_LEVELS];
-    dim3 g((A + 255) / 256, B);
-    { YcrProfScope ps(YCR_T_DECODE, st); k_decode<<<g, 256, 0, st>>>(d, allpred); }
+    bool vec = (reinterpret_cast<uintptr_t>(allpred) % 16 == 0);
+    for (int l = 0; l < grid->n_levels; ++l)
+        vec = vec && (grid->w[l] % 4 == 0) && (reinterpret_cast<uintptr_t>(feats[l]) % 16 == 0);
+    if (vec) {
+        dim3 g((A / 4 + 255) / 256, B);
+        YcrProfScope ps(YCR_T_DECODE, st);
+        k_decode_v4<<<g, 256, 0, st>>>(d, allpred);
+    } else {
+        dim3 g((A + 255) / 256, B);
+        YcrProfScope ps(YCR_T_DECODE, st);
+        k_decode<<<g, 256, 0, st>>>(d, allpred);
+    }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }

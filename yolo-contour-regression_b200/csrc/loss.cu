@@ -72,28 +72,116 @@ __global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ A
     }
 }
 
-// total = (box_gain*l_box + cls_gain*l_cls) * B  (utils/loss.py:874-878); fixed-order reductions.
-__global__ void __launch_bounds__(256) k_loss_finalize(AssignWs ws, int B, int n_bce, float box_gain, float cls_gain,
-                                                       float* loss_out) {
-    __shared__ double s_b[256], s_p[256];
-    const int tid = threadIdx.x;
-    double sb = 0.0, sp = 0.0;
-    for (int i = tid; i < n_bce; i += 256) sb += (double)ws.bce_part[i];
-    for (int b = 0; b < B; ++b) {
-        const int n = ws.npos[b];
-        for (int r = tid; r < n; r += 256) sp += (double)ws.pos_loss[(int64_t)b * ws.pos_cap + r];
+// Vectorised variant (every level's H*W is a multiple of 4, true for all image sizes divisible by 64):
+// one thread per FOUR consecutive anchors, 128-bit loads and stores, four channels in flight.
+__device__ __forceinline__ float bce_term(float x, float t, float gscale, float& grad) {
+    const float e = __expf(-fabsf(x));
+    const float r = __fdividef(1.f, 1.f + e);
+    const float sig = (x >= 0.f) ? r : e * r;
+    grad = (sig - t) * gscale;
+    return fmaxf(x, 0.f) - x * t + log1pf(e);
+}
+
+__global__ void __launch_bounds__(K5_NT) k_loss_stream_v4(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                                          const float* f0, const float* f1, const float* f2, const float* f3,
+                                                          float* g0, float* g1, float* g2, float* g3, float cls_gain) {
+    __shared__ float s_red[K5_NT / 32];
+    const int A = a.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.y;
+    const int an = (blockIdx.x * K5_NT + threadIdx.x) * 4;
+    const int R = a.cfg.rays, nc = a.cfg.num_classes;
+    float acc = 0.f;
+    if (an < A) {
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+            if (k < a.grid.n_levels && an >= a.grid.off[k]) l = k;
+        const float* f = (l == 0) ? f0 : (l == 1) ? f1 : (l == 2) ? f2 : f3;
+        float* g = (l == 0) ? g0 : (l == 1) ? g1 : (l == 2) ? g2 : g3;
+        const int hw = a.grid.h[l] * a.grid.w[l];
+        const int al = an - a.grid.off[l];
+        const int64_t base = (int64_t)b * (R + nc) * hw + al;
+        const int4 rows = *reinterpret_cast<const int4*>(ws.pos_row + (int64_t)b * A + an);
+        const int row[4] = {rows.x, rows.y, rows.z, rows.w};
+        int label[4] = {-1, -1, -1, -1};
+        float tn[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* pg[4] = {nullptr, nullptr, nullptr, nullptr};
+        const bool any_pos = (rows.x & rows.y & rows.z & rows.w) >= 0;  // some row index is non-negative
+        if (any_pos) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (row[k] >= 0) {
+                    const int gi = ws.pos_g[(int64_t)b * ws.pos_cap + row[k]];
+                    const int64_t lab = (int64_t)a.gt.labels[(int64_t)(b * a.gt.G + gi) * a.gt.labels_stride];
+                    label[k] = (int)(lab < 0 ? 0 : lab);
+                    tn[k] = ws.pos_norm[(int64_t)b * ws.pos_cap + row[k]];
+                    pg[k] = ws.pos_grad + ((int64_t)b * ws.pos_cap + row[k]) * R;
+                }
+            }
+        }
+        const float gscale = cls_gain * (float)a.gt.B / ws.tss[0];
+        if (g) {
+            if (any_pos) {
+                for (int i = 0; i < R; ++i) {
+                    float4 v;
+                    v.x = pg[0] ? pg[0][i] : 0.f; v.y = pg[1] ? pg[1][i] : 0.f;
+                    v.z = pg[2] ? pg[2][i] : 0.f; v.w = pg[3] ? pg[3][i] : 0.f;
+                    __stcs(reinterpret_cast<float4*>(g + base + (int64_t)i * hw), v);
+                }
+            } else {
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int i = 0; i < R; ++i) __stcs(reinterpret_cast<float4*>(g + base + (int64_t)i * hw), z);
+            }
+        }
+        const float* fc = f + base + (int64_t)R * hw;
+        float* gc = g ? g + base + (int64_t)R * hw : nullptr;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+            const float4 x = __ldcs(reinterpret_cast<const float4*>(fc + (int64_t)c * hw));
+            float4 gr;
+            acc += bce_term(x.x, (c == label[0]) ? tn[0] : 0.f, gscale, gr.x);
+            acc += bce_term(x.y, (c == label[1]) ? tn[1] : 0.f, gscale, gr.y);
+            acc += bce_term(x.z, (c == label[2]) ? tn[2] : 0.f, gscale, gr.z);
+            acc += bce_term(x.w, (c == label[3]) ? tn[3] : 0.f, gscale, gr.w);
+            if (gc) __stcs(reinterpret_cast<float4*>(gc + (int64_t)c * hw), gr);
+        }
     }
-    s_b[tid] = sb;
-    s_p[tid] = sp;
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) { s_b[tid] += s_b[tid + o]; s_p[tid] += s_p[tid + o]; }
-        __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < K5_NT / 32) ? s_red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) ws.bce_part[blockIdx.y * gridDim.x + blockIdx.x] = v;
     }
+}
+
+// total = (box_gain*l_box + cls_gain*l_cls) * B  (utils/loss.py:874-878); fixed-order reductions:
+// warp w sums images w, w+32, ... and partials w, w+32.., then one fixed tree over the 32 warps.
+__global__ void __launch_bounds__(1024) k_loss_finalize(AssignWs ws, int B, int n_bce, float box_gain, float cls_gain,
+                                                        float* loss_out) {
+    __shared__ double s_b[32], s_p[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double sb = 0.0, sp = 0.0;
+    for (int i = tid; i < n_bce; i += 1024) sb += (double)ws.bce_part[i];
+    for (int b = warp; b < B; b += 32) {
+        const int n = ws.npos[b];
+        for (int r = lane; r < n; r += 32) sp += (double)ws.pos_loss[(int64_t)b * ws.pos_cap + r];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        sp += __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    if (lane == 0) { s_b[warp] = sb; s_p[warp] = sp; }
+    __syncthreads();
     if (tid == 0) {
+        double tb = 0.0, tp = 0.0;
+        for (int w = 0; w < 32; ++w) { tb += s_b[w]; tp += s_p[w]; }
         const double tss = (double)ws.tss[0];
-        const float l_box = (float)(s_p[0] / tss) * box_gain;
-        const float l_cls = (float)(s_b[0] / tss) * cls_gain;
+        const float l_box = (float)(tp / tss) * box_gain;
+        const float l_cls = (float)(tb / tss) * cls_gain;
         loss_out[0] = (l_box + l_cls) * (float)B;
         loss_out[1] = l_box;
         loss_out[2] = l_cls;
@@ -107,14 +195,27 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* con
     const int A = a.grid.off[YCR_MAX_LEVELS];
     const float* f[4] = {nullptr, nullptr, nullptr, nullptr};
     float* g[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool vec = true;
     for (int l = 0; l < a.grid.n_levels; ++l) {
         f[l] = feats[l];
         g[l] = grads ? grads[l] : nullptr;
+        vec = vec && ((a.grid.h[l] * a.grid.w[l]) % 4 == 0) && (reinterpret_cast<uintptr_t>(f[l]) % 16 == 0) &&
+              (!g[l] || reinterpret_cast<uintptr_t>(g[l]) % 16 == 0);
     }
-    dim3 grid((A + K5_NT - 1) / K5_NT, B);
-    { YcrProfScope ps(YCR_T_STREAM, st); k_loss_stream<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain); }
+    int nblk;
+    if (vec) {
+        dim3 grid((A / 4 + K5_NT - 1) / K5_NT, B);
+        nblk = (int)(grid.x * grid.y);
+        YcrProfScope ps(YCR_T_STREAM, st);
+        k_loss_stream_v4<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain);
+    } else {
+        dim3 grid((A + K5_NT - 1) / K5_NT, B);
+        nblk = (int)(grid.x * grid.y);
+        YcrProfScope ps(YCR_T_STREAM, st);
+        k_loss_stream<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain);
+    }
     YCR_LAUNCH_CHECK();
-    { YcrProfScope ps(YCR_T_FINAL, st); k_loss_finalize<<<1, 256, 0, st>>>(ws, B, (int)(grid.x * grid.y), lcfg.box_gain, lcfg.cls_gain, loss_out); }
+    { YcrProfScope ps(YCR_T_FINAL, st); k_loss_finalize<<<1, 1024, 0, st>>>(ws, B, nblk, lcfg.box_gain, lcfg.cls_gain, loss_out); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
