@@ -61,8 +61,9 @@ __global__ void __launch_bounds__(256) k_decode(const __grid_constant__ DecodeAr
 }
 
 // Vectorised variant: one thread per four consecutive anchors of a row (W_l and H_l*W_l multiples of 4),
-// 128-bit loads/stores.
-__global__ void __launch_bounds__(256) k_decode_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
+// 128-bit loads/stores.  Split in two kernels so that the class part (pure streaming sigmoid) is not
+// held to the occupancy of the ray part (which carries the 16 running box extrema).
+__global__ void __launch_bounds__(256, 3) k_decode_rays_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
     const int A = d.grid.off[YCR_MAX_LEVELS];
     const int b = blockIdx.y;
     const int an = (blockIdx.x * 256 + threadIdx.x) * 4;
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(256) k_decode_v4(const __grid_constant__ Decod
     float* o = out + (int64_t)b * CH * A + an;
     float4 minx = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f), miny = minx;
     float4 maxx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), maxy = maxx;
-#pragma unroll 4
+#pragma unroll 2
     for (int i = 0; i < R; ++i) {
         const float4 r = __ldcs(reinterpret_cast<const float4*>(f + (int64_t)i * hw));
         const float c = d.cs[i], s = d.cs[R + i];
@@ -109,14 +110,32 @@ __global__ void __launch_bounds__(256) k_decode_v4(const __grid_constant__ Decod
     *reinterpret_cast<float4*>(o + (int64_t)A) = miny;
     *reinterpret_cast<float4*>(o + (int64_t)2 * A) = maxx;
     *reinterpret_cast<float4*>(o + (int64_t)3 * A) = maxy;
-    const float* fc = f + (int64_t)R * hw;
-#pragma unroll 4
-    for (int c = 0; c < nc; ++c) {
+}
+
+// class rows: grid (anchor groups, class groups of 8, B)
+__global__ void __launch_bounds__(256) k_decode_cls_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
+    const int A = d.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.z;
+    const int an = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (an >= A) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+        if (k < d.grid.n_levels && an >= d.grid.off[k]) l = k;
+    const int hw = d.grid.h[l] * d.grid.w[l];
+    const int al = an - d.grid.off[l];
+    const int R = d.R, nc = d.nc;
+    const int CH = 4 + nc + 3 * R;
+    const int c0 = blockIdx.y * 8, c1 = min(nc, c0 + 8);
+    const float* fc = d.feats[l] + (int64_t)b * (R + nc) * hw + (int64_t)R * hw + al;
+    float* o = out + (int64_t)b * CH * A + an;
+#pragma unroll 8
+    for (int c = c0; c < c1; ++c) {
         const float4 x = __ldcs(reinterpret_cast<const float4*>(fc + (int64_t)c * hw));
         float4 p;
         p.x = 1.f / (1.f + expf(-x.x)); p.y = 1.f / (1.f + expf(-x.y));
         p.z = 1.f / (1.f + expf(-x.z)); p.w = 1.f / (1.f + expf(-x.w));
-        *reinterpret_cast<float4*>(o + (int64_t)(4 + c) * A) = p;   // class rows are re-read by NMS: keep in L2
+        *reinterpret_cast<float4*>(o + (int64_t)(4 + c) * A) = p;   // class rows are re-read by NMS
     }
 }
 
@@ -138,8 +157,10 @@ int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int 
         vec = vec && (grid->w[l] % 4 == 0) && (reinterpret_cast<uintptr_t>(feats[l]) % 16 == 0);
     if (vec) {
         dim3 g((A / 4 + 255) / 256, B);
+        dim3 gc((A / 4 + 255) / 256, (nc + 7) / 8, B);
         YcrProfScope ps(YCR_T_DECODE, st);
-        k_decode_v4<<<g, 256, 0, st>>>(d, allpred);
+        k_decode_rays_v4<<<g, 256, 0, st>>>(d, allpred);
+        k_decode_cls_v4<<<gc, 256, 0, st>>>(d, allpred);
     } else {
         dim3 g((A + 255) / 256, B);
         YcrProfScope ps(YCR_T_DECODE, st);
@@ -287,39 +308,37 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
 }
 
 #define NMS_NT 256
-#define NMS_MAX_SUPWORDS 1024  // 32768 boxes
+#define NMS_MAX_KEEP 1024
 
-// per image greedy suppression in chunks of 64 sorted boxes: (A) 64x64 bitmask inside the chunk,
-// (B) one thread walks the chunk sequentially with bit operations, (C) the boxes kept in this
-// chunk suppress every later box in parallel.  Then the kept rows are gathered:
-// [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 408, 418).
+// per image greedy suppression over the sorted candidates, 64 at a time ("pull" form of
+// torchvision's greedy loop: a box is kept iff no EARLIER KEPT box overlaps it by more than thr):
+//   (P) the 64 boxes of the chunk are tested against every box kept so far (4 threads per box),
+//   (A) 64x64 bitmask inside the chunk,
+//   (B) one thread walks the chunk in score order with bit operations and appends the survivors.
+// The loop ends when max_det boxes are kept (utils/ops.py:408), so boxes after the max_det-th
+// survivor are never touched.  Then the kept rows are gathered:
+// [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 418).
 __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
                                                          float* __restrict__ out_rows, int* __restrict__ out_counts) {
-    __shared__ unsigned s_sup[NMS_MAX_SUPWORDS];
+    __shared__ float4 s_kbox[NMS_MAX_KEEP];
+    __shared__ int s_kept[NMS_MAX_KEEP];
     __shared__ unsigned long long s_mask[64];
     __shared__ float4 s_box[64];
-    __shared__ float4 s_kbox[64];
-    __shared__ int s_kept[1024];
-    __shared__ int s_nk_chunk, s_nkept;
+    __shared__ unsigned long long s_dead;
+    __shared__ int s_nkept, s_cut;
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n = min(min(ws.count[b], ws.cap), ws.nsel_cap);
-    const int max_det = min(cfg.max_det, 1024);
+    const int max_det = min(cfg.max_det, NMS_MAX_KEEP);
     const float4* boxes = ws.boxes + (int64_t)b * ws.nsel_cap;
     const unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
-    // entries of filtered-out classes sorted to the end: drop them
-    int n_eff = n;
-    if (cfg.classes) {
-        __shared__ int s_cut;
-        if (tid == 0) s_cut = n;
-        __syncthreads();
+    if (tid == 0) { s_nkept = 0; s_cut = n; }
+    __syncthreads();
+    if (cfg.classes) {  // entries of filtered-out classes were sorted to the end: drop them
         for (int i = tid; i < n; i += NMS_NT)
             if (keys[i] == 0xFFFFFFFFFFFFFFFFull) atomicMin(&s_cut, i);
         __syncthreads();
-        n_eff = s_cut;
     }
-    for (int i = tid; i < ((n_eff + 63) / 64) * 2 + 2 && i < NMS_MAX_SUPWORDS; i += NMS_NT) s_sup[i] = 0;
-    if (tid == 0) s_nkept = 0;
-    __syncthreads();
+    const int n_eff = s_cut;
     const float thr = cfg.iou_thres;
     for (int c0 = 0; c0 < n_eff; c0 += 64) {
         const int cn = min(64, n_eff - c0);
@@ -327,56 +346,46 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
             s_mask[tid] = 0ull;
             if (tid < cn) s_box[tid] = boxes[c0 + tid];
         }
+        if (tid == 0) s_dead = 0ull;
         __syncthreads();
-        {   // (A) thread -> row i, 16 columns
-            const int i = tid >> 2, q = tid & 3;
-            if (i < cn) {
-                const float4 bi = s_box[i];
-                const float ai = __fmul_rn(bi.z - bi.x, bi.w - bi.y);
-                unsigned long long m = 0ull;
-                for (int j = q * 16; j < q * 16 + 16; ++j)
-                    if (j > i && j < cn && iou_gt(bi, ai, s_box[j], thr)) m |= (1ull << j);
-                if (m) atomicOr(&s_mask[i], m);
+        const int nk = s_nkept;
+        const int i = tid >> 2, q = tid & 3;
+        if (i < cn) {
+            const float4 bi = s_box[i];
+            const float ai = __fmul_rn(bi.z - bi.x, bi.w - bi.y);
+            // (P) against the boxes kept so far; kept box is the first IoU operand as in the reference loop
+            bool dead = false;
+            for (int k = q; k < nk && !dead; k += 4) {
+                const float4 bk = s_kbox[k];
+                const float ak = __fmul_rn(bk.z - bk.x, bk.w - bk.y);
+                const float w = fmaxf(0.f, fminf(bk.z, bi.z) - fmaxf(bk.x, bi.x));
+                const float h = fmaxf(0.f, fminf(bk.w, bi.w) - fmaxf(bk.y, bi.y));
+                const float inter = __fmul_rn(w, h);
+                dead = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, ai), inter)) > thr;
             }
+            if (dead) atomicOr(&s_dead, 1ull << i);
+            // (A) inside the chunk: row i, 16 columns per thread
+            unsigned long long m = 0ull;
+            for (int j = q * 16; j < q * 16 + 16; ++j)
+                if (j > i && j < cn && iou_gt(bi, ai, s_box[j], thr)) m |= (1ull << j);
+            if (m) atomicOr(&s_mask[i], m);
         }
         __syncthreads();
         if (tid == 0) {  // (B)
-            unsigned long long sup = (unsigned long long)s_sup[c0 >> 5] | ((unsigned long long)s_sup[(c0 >> 5) + 1] << 32);
-            int nk = 0, total = s_nkept;
-            for (int i = 0; i < cn && total < max_det; ++i) {
-                if (!((sup >> i) & 1ull)) {
-                    s_kbox[nk] = s_box[i];
-                    s_kept[total] = c0 + i;
-                    ++nk; ++total;
-                    sup |= s_mask[i];
+            unsigned long long sup = s_dead;
+            int total = nk;
+            for (int r = 0; r < cn && total < max_det; ++r) {
+                if (!((sup >> r) & 1ull)) {
+                    s_kbox[total] = s_box[r];
+                    s_kept[total] = c0 + r;
+                    ++total;
+                    sup |= s_mask[r];
                 }
             }
-            s_nk_chunk = nk;
             s_nkept = total;
         }
         __syncthreads();
         if (s_nkept >= max_det) break;
-        const int nk = s_nk_chunk;
-        if (nk > 0) {  // (C)
-            for (int j = c0 + 64 + tid; j < n_eff; j += NMS_NT) {
-                if ((s_sup[j >> 5] >> (j & 31)) & 1u) continue;
-                const float4 bj = boxes[j];
-                const float aj = __fmul_rn(bj.z - bj.x, bj.w - bj.y);
-                bool dead = false;
-                for (int k = 0; k < nk && !dead; ++k) {
-                    const float4 bk = s_kbox[k];
-                    // same operand order as the reference loop: kept box i first
-                    const float ak = __fmul_rn(bk.z - bk.x, bk.w - bk.y);
-                    const float w = fmaxf(0.f, fminf(bk.z, bj.z) - fmaxf(bk.x, bj.x));
-                    const float h = fmaxf(0.f, fminf(bk.w, bj.w) - fmaxf(bk.y, bj.y));
-                    const float inter = __fmul_rn(w, h);
-                    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, aj), inter));
-                    dead = iou > thr;
-                }
-                if (dead) atomicOr(&s_sup[j >> 5], 1u << (j & 31));
-            }
-        }
-        __syncthreads();
     }
     __syncthreads();
     const int nk = s_nkept;
@@ -384,19 +393,25 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
     const int nc = cfg.nc, nm = CH - 4 - nc, W = 6 + nm;
     const float* p = pred + (int64_t)b * CH * A;
     float* o = out_rows + (int64_t)b * cfg.max_det * W;
-    for (int e = tid; e < nk * W; e += NMS_NT) {
-        const int r = e / W, col = e - r * W;
+    // one warp per kept row, lanes over the output columns (independent scattered loads in flight)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < nk; r += NMS_NT / 32) {
         const unsigned long long k = keys[s_kept[r]];
         const unsigned idx = (unsigned)(k & 0xFFFFFFFFull);
         const int an = idx / nc, c = idx - an * nc;
-        float v;
-        if (col < 4) v = p[(int64_t)col * A + an];
-        else if (col == 4) v = __uint_as_float(~(unsigned)(k >> 32));
-        else if (col == 5) v = (float)c;
-        else v = p[(int64_t)(4 + nc + col - 6) * A + an];
-        o[(int64_t)r * W + col] = v;
+        const float score = __uint_as_float(~(unsigned)(k >> 32));
+#pragma unroll 4
+        for (int col = lane; col < W; col += 32) {
+            float v;
+            if (col < 4) v = p[(int64_t)col * A + an];
+            else if (col == 4) v = score;
+            else if (col == 5) v = (float)c;
+            else v = p[(int64_t)(4 + nc + col - 6) * A + an];
+            o[(int64_t)r * W + col] = v;
+        }
     }
 }
+
 
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_ws_layout(nullptr, nullptr, B, A, cfg); }
 
@@ -405,7 +420,6 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
     NmsWs ws;
     const size_t need = nms_ws_layout(&ws, workspace, B, A, cfg);
     if (need > workspace_bytes) { ycr_set_error("nms workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
-    if (ws.nsel_cap > NMS_MAX_SUPWORDS * 32) { ycr_set_error("max_nms %d above supported %d", ws.nsel_cap, NMS_MAX_SUPWORDS * 32); return YCR_E_ARG; }
     YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
     dim3 g((A + 255) / 256, B);
     { YcrProfScope ps(YCR_T_NMS_FILTER, st); k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws); }
