@@ -177,6 +177,7 @@ struct NmsWs {
     unsigned long long* keys;  // [B][cap2]  (~score bits << 32) | (anchor*nc + class), sorted ascending
     int* count;                // [B] candidates written (may exceed cap)
     float4* boxes;             // [B][nsel_cap] class-offset boxes in sorted order
+    int4* kept;                // [B][NMS_MAX_KEEP] (anchor, class, score bits, -) of the kept rows
     int cap, cap2, nsel_cap;
 };
 
@@ -193,6 +194,7 @@ static size_t nms_ws_layout(NmsWs* ws, void* base, int B, int A, const ycr_nms_c
     w.keys = al.take<unsigned long long>((size_t)B * w.cap2);
     w.count = al.take<int>(B + 1);
     w.boxes = al.take<float4>((size_t)B * w.nsel_cap + 1);
+    w.kept = al.take<int4>((size_t)B * 1024);
     if (ws) *ws = w;
     return align_up(al.off, 256);
 }
@@ -390,28 +392,37 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
     __syncthreads();
     const int nk = s_nkept;
     if (tid == 0) out_counts[b] = nk;
-    const int nc = cfg.nc, nm = CH - 4 - nc, W = 6 + nm;
-    const float* p = pred + (int64_t)b * CH * A;
-    float* o = out_rows + (int64_t)b * cfg.max_det * W;
-    // one warp per kept row, lanes over the output columns (independent scattered loads in flight)
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int r = warp; r < nk; r += NMS_NT / 32) {
+    const int nc = cfg.nc;
+    // hand the kept list to the gather kernel: sorted position -> (anchor, class, score)
+    int4* ko = ws.kept + (int64_t)b * NMS_MAX_KEEP;
+    for (int r = tid; r < nk; r += NMS_NT) {
         const unsigned long long k = keys[s_kept[r]];
         const unsigned idx = (unsigned)(k & 0xFFFFFFFFull);
-        const int an = idx / nc, c = idx - an * nc;
-        const float score = __uint_as_float(~(unsigned)(k >> 32));
-#pragma unroll 4
-        for (int col = lane; col < W; col += 32) {
-            float v;
-            if (col < 4) v = p[(int64_t)col * A + an];
-            else if (col == 4) v = score;
-            else if (col == 5) v = (float)c;
-            else v = p[(int64_t)(4 + nc + col - 6) * A + an];
-            o[(int64_t)r * W + col] = v;
-        }
+        const int an = idx / nc;
+        ko[r] = make_int4(an, (int)(idx - an * nc), (int)(~(unsigned)(k >> 32)), 0);
     }
 }
 
+// kept rows [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 418): the input is
+// channel-major, so every element of a row is its own 32-byte sector; one thread per element keeps as
+// many of those scattered loads in flight as the machine allows.
+__global__ void __launch_bounds__(256) k_nms_gather(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
+                                                    const int* __restrict__ counts, float* __restrict__ out_rows) {
+    const int b = blockIdx.y;
+    const int nc = cfg.nc, W = CH - 4 - nc + 6;
+    const int nk = counts[b];
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= nk * W) return;
+    const int r = e / W, col = e - r * W;
+    const int4 k = ws.kept[(int64_t)b * NMS_MAX_KEEP + r];
+    const float* p = pred + (int64_t)b * CH * A + k.x;
+    float v;
+    if (col < 4) v = p[(int64_t)col * A];
+    else if (col == 4) v = __int_as_float(k.z);
+    else if (col == 5) v = (float)k.y;
+    else v = p[(int64_t)(4 + nc + col - 6) * A];
+    out_rows[((int64_t)b * cfg.max_det + r) * W + col] = v;
+}
 
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_ws_layout(nullptr, nullptr, B, A, cfg); }
 
@@ -426,7 +437,14 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
     YCR_LAUNCH_CHECK();
     { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws); }
     YCR_LAUNCH_CHECK();
-    { YcrProfScope ps(YCR_T_NMS_SUPPRESS, st); k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts); }
+    {
+        YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
+        k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts);
+        const int maxk = cfg->max_det < NMS_MAX_KEEP ? cfg->max_det : NMS_MAX_KEEP;
+        const int W = CH - 4 - cfg->nc + 6;
+        dim3 gg((maxk * W + 255) / 256, B);
+        k_nms_gather<<<gg, 256, 0, st>>>(prediction, CH, A, *cfg, ws, out_counts, out_rows);
+    }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
