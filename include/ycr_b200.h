@@ -163,6 +163,20 @@ int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* g
 int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,
                      float* out_packed, void* stream);
 
+/* Box terms kept for API coverage (dormant on the live polar path): replaces BboxLoss.forward
+ * (utils/loss.py:61-75) with _df_loss (:77-87), bbox_iou(CIoU) (utils/metrics.py:77-130) and bbox2dist
+ * (utils/tal.py:1437-1440), forward and gradient in one pass.
+ *   pred_dist (B,A,4*(reg_max+1)) logits, pred_bboxes/target_bboxes (B,A,4) xyxy, anchor_points (A,2),
+ *   target_scores (B,A,nc), fg_mask (B,A) bool, target_scores_sum_d device scalar.
+ *   loss_out device float[2] = {loss_iou, loss_dfl}; grad_* same shapes as the inputs, fully overwritten
+ *   (d(loss_iou + loss_dfl)/d input), may be NULL. */
+size_t ycr_bbox_loss_workspace_bytes(int B, int A);
+int ycr_bbox_loss_fwd_bwd(const float* pred_dist, const float* pred_bboxes, const float* anchor_points,
+                          const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask,
+                          const float* target_scores_sum_d, int B, int A, int nc, int reg_max, int use_dfl,
+                          float* loss_out, float* grad_pred_dist, float* grad_pred_bboxes, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- inference path -------------------------------------------------------------------------- */
 
 /* Replaces Segment.forward eval branch / distance2mask (nn/modules/head.py:461-494, 559-570):

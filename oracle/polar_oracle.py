@@ -462,3 +462,50 @@ def nms(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=Fals
         margin = min(margin, m)
         output[xi] = x[torch.from_numpy(keep[:max_det])]
     return output, margin
+
+
+# --------------------------------------------------------------------------------------------
+# dormant box terms: CIoU + DFL (BboxLoss)
+# --------------------------------------------------------------------------------------------
+def bbox_ciou(box1, box2, eps: float = 1e-7):
+    """utils/metrics.py:77-130 bbox_iou(xywh=False, CIoU=True)"""
+    b1_x1, b1_y1, b1_x2, b1_y2 = box1.chunk(4, -1)
+    b2_x1, b2_y1, b2_x2, b2_y2 = box2.chunk(4, -1)
+    w1, h1 = b1_x2 - b1_x1, b1_y2 - b1_y1 + eps
+    w2, h2 = b2_x2 - b2_x1, b2_y2 - b2_y1 + eps
+    inter = (torch.minimum(b1_x2, b2_x2) - torch.maximum(b1_x1, b2_x1)).clamp(0) * \
+            (torch.minimum(b1_y2, b2_y2) - torch.maximum(b1_y1, b2_y1)).clamp(0)
+    union = w1 * h1 + w2 * h2 - inter + eps
+    iou = inter / union
+    cw = torch.maximum(b1_x2, b2_x2) - torch.minimum(b1_x1, b2_x1)
+    ch = torch.maximum(b1_y2, b2_y2) - torch.minimum(b1_y1, b2_y1)
+    c2 = cw ** 2 + ch ** 2 + eps
+    rho2 = ((b2_x1 + b2_x2 - b1_x1 - b1_x2) ** 2 + (b2_y1 + b2_y2 - b1_y1 - b1_y2) ** 2) / 4
+    v = (4 / math.pi ** 2) * (torch.atan(w2 / h2) - torch.atan(w1 / h1)).pow(2)
+    with torch.no_grad():
+        alpha = v / (v - iou + (1 + eps))
+    return iou - (rho2 / c2 + v * alpha)
+
+
+def bbox_loss(pred_dist, pred_bboxes, anchor_points, target_bboxes, target_scores, target_scores_sum, fg_mask,
+              reg_max: int = 15, use_dfl: bool = True):
+    """utils/loss.py:61-87 BboxLoss.forward + _df_loss; bbox2dist utils/tal.py:1437-1440.
+    reg_max here is BboxLoss.reg_max (= head reg_max - 1, i.e. 15)."""
+    weight = target_scores.sum(-1)[fg_mask].unsqueeze(-1)
+    iou = bbox_ciou(pred_bboxes[fg_mask], target_bboxes[fg_mask])
+    loss_iou = ((1.0 - iou) * weight).sum() / target_scores_sum
+    loss_dfl = torch.tensor(0.0)
+    if use_dfl:
+        x1y1, x2y2 = target_bboxes.chunk(2, -1)
+        ltrb = torch.cat((anchor_points - x1y1, x2y2 - anchor_points), -1).clamp(0, reg_max - 0.01)
+        pd = pred_dist[fg_mask].view(-1, reg_max + 1)
+        tgt = ltrb[fg_mask]
+        tl = tgt.long()
+        tr = tl + 1
+        wl = tr - tgt
+        wr = 1 - wl
+        ce = torch.nn.functional.cross_entropy
+        dfl = (ce(pd, tl.view(-1), reduction="none").view(tl.shape) * wl +
+               ce(pd, tr.view(-1), reduction="none").view(tl.shape) * wr).mean(-1, keepdim=True)
+        loss_dfl = (dfl * weight).sum() / target_scores_sum
+    return loss_iou, loss_dfl

@@ -182,6 +182,29 @@ def main():
     print("kat_circle: P", out[5].shape[0], "centre score", float(out[2][0, ci, 1]),
           "gt_dist range", float(out[5].min()), float(out[5].max()), flush=True)
 
+    # ---------------- dormant box terms: BboxLoss (CIoU + DFL), utils/loss.py:53-87 ----------------
+    g = torch.Generator().manual_seed(123)
+    B, A, nc, reg = 2, 525, 10, 15
+    from oracle import polar_oracle as po
+    anc, _ = po.make_anchors([(20, 20), (10, 10), (5, 5)], [8, 16, 32])   # grid units, as the reference passes them
+    xy = torch.rand(B, A, 2, generator=g) * 12 + 2
+    wh = torch.rand(B, A, 2, generator=g) * 6 + 1
+    tb = torch.cat([xy - wh, xy + wh], -1)
+    pb = (tb + torch.randn(B, A, 4, generator=g) * 0.7).requires_grad_(True)
+    pd = torch.randn(B, A, 4 * (reg + 1), generator=g).requires_grad_(True)
+    fg = torch.rand(B, A, generator=g) < 0.08
+    ts = torch.zeros(B, A, nc)
+    ts[fg] = torch.rand(int(fg.sum()), nc, generator=g) * (torch.rand(int(fg.sum()), nc, generator=g) < 0.15)
+    tss = max(ts.sum(), 1)
+    li, ld = rloss.BboxLoss(reg, use_dfl=True)(pd, pb, anc, tb, ts, tss, fg)
+    (li * 7.5 + ld * 1.5).backward()
+    np.savez_compressed(os.path.join(HERE, "bbox_loss.npz"), pred_dist=pd.detach().numpy(),
+                        pred_bboxes=pb.detach().numpy(), anchor_points=anc.numpy(), target_bboxes=tb.numpy(),
+                        target_scores=ts.numpy(), fg_mask=fg.numpy(), tss=np.float32(tss),
+                        loss_iou=li.detach().numpy(), loss_dfl=ld.detach().numpy(), grad_dist=pd.grad.numpy(),
+                        grad_bboxes=pb.grad.numpy(), gains=np.array([7.5, 1.5], np.float32))
+    print("bbox_loss", float(li), float(ld), int(fg.sum()), flush=True)
+
     # ---------------- inference path ----------------
     infer_cases = [
         ("infer_s160", synth.PathConfig("s160", 2, 0, 160, nc=10), 21, True),

@@ -249,3 +249,48 @@ def test_batch_scale_matches_oracle_on_sampled_images():
         ok = ~ref["gt_dist_ambiguous"]
         assert rel_err(rows[ok], ref["gt_dist"][ok]) < TOL
     assert checked >= 1
+
+
+def test_bbox_loss_ciou_dfl_matches_reference():
+    """Row 15 of SURVEY §8-a (dormant on the live path): BboxLoss forward + gradients vs the reference."""
+    from ycr_b200.loss import BboxLoss
+    dev = _dev()
+    g = load_golden("bbox_loss")
+    pd = torch.from_numpy(g["pred_dist"]).to(dev).requires_grad_(True)
+    pb = torch.from_numpy(g["pred_bboxes"]).to(dev).requires_grad_(True)
+    crit = BboxLoss(15, use_dfl=True)
+    li, ld = crit(pd, pb, torch.from_numpy(g["anchor_points"]).to(dev), torch.from_numpy(g["target_bboxes"]).to(dev),
+                  torch.from_numpy(g["target_scores"]).to(dev), float(g["tss"]), torch.from_numpy(g["fg_mask"]).to(dev))
+    (li * float(g["gains"][0]) + ld * float(g["gains"][1])).backward()
+    assert rel_err(li.detach().cpu(), g["loss_iou"]) < TOL
+    assert rel_err(ld.detach().cpu(), g["loss_dfl"]) < TOL
+    gd, gb = torch.from_numpy(g["grad_dist"]), torch.from_numpy(g["grad_bboxes"])
+    assert float((pd.grad.cpu() - gd).abs().max()) <= TOL * float(gd.abs().max())
+    assert float((pb.grad.cpu() - gb).abs().max()) <= TOL * float(gb.abs().max())
+    assert torch.equal(pd.grad.cpu() != 0, gd != 0)                 # only foreground anchors get gradients
+    # DFL switched off: loss_dfl is 0 and pred_dist gets no gradient
+    pb2 = torch.from_numpy(g["pred_bboxes"]).to(dev).requires_grad_(True)
+    li2, ld2 = BboxLoss(15, use_dfl=False)(pd.detach(), pb2, torch.from_numpy(g["anchor_points"]).to(dev),
+                                           torch.from_numpy(g["target_bboxes"]).to(dev),
+                                           torch.from_numpy(g["target_scores"]).to(dev), float(g["tss"]),
+                                           torch.from_numpy(g["fg_mask"]).to(dev))
+    assert float(ld2) == 0.0 and rel_err(li2.detach().cpu(), g["loss_iou"]) < TOL
+
+
+def test_pack_targets_kernel_matches_oracle():
+    """GT packing kernel (v8DetectionLoss.preprocess, utils/loss.py:215-239) incl. ragged and shuffled rows."""
+    from ycr_b200.loss import v8SegmentationLoss
+    from ycr_b200 import synth
+    dev = _dev()
+    cfg = synth.PathConfig("p", 5, 7, 320, nc=10)
+    batch = synth.make_gts(cfg, 61, ragged=True)
+    crit = v8SegmentationLoss(nc=cfg.nc, nm=cfg.rays, strides=cfg.strides, device=dev)
+    crit._shapes = cfg.level_shapes
+    packed, cap = crit.pack_targets(batch, cfg.batch, (320, 320))
+    ref = po.pack_targets(batch, cfg.batch, (320, 320))
+    assert packed.shape == ref.shape
+    assert rel_err(packed.cpu(), ref, floor=1e-3) < 1e-6
+    assert torch.equal(packed.cpu()[..., 0], ref[..., 0])
+    m = po.in_box_mask((po.make_anchors(cfg.level_shapes, cfg.strides)[0] * po.make_anchors(cfg.level_shapes, cfg.strides)[1]),
+                       ref[..., 1:5])
+    assert int(m.sum()) <= cap                                       # host bound really is an upper bound

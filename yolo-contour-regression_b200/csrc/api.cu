@@ -34,6 +34,11 @@ void ycr_prof_mark(int tag, int end, cudaStream_t st) {
 }
 
 int debug_stats(unsigned long long* out_h, int reset);
+size_t bbox_loss_workspace_bytes(int B, int A);
+int launch_bbox_loss(const float* pred_dist, const float* pred_bboxes, const float* anchor_points,
+                     const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* tss_d,
+                     int B, int A, int nc, int reg_max, int use_dfl, float* loss_out, float* grad_dist, float* grad_bboxes,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st);
 int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
                         cudaStream_t st);
@@ -186,6 +191,21 @@ int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int
     if (B < 1 || G < 0 || row_stride < 6 + 2 * YCR_C) { ycr_set_error("bad B/G/row_stride"); return YCR_E_ARG; }
     if (G == 0) return YCR_OK;
     return launch_pack_targets(targets, row_stride, N, B, G, img_w, img_h, out_packed, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ycr_bbox_loss_workspace_bytes(int B, int A) { return (B > 0 && A > 0) ? bbox_loss_workspace_bytes(B, A) : 0; }
+
+int ycr_bbox_loss_fwd_bwd(const float* pred_dist, const float* pred_bboxes, const float* anchor_points,
+                          const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask,
+                          const float* target_scores_sum_d, int B, int A, int nc, int reg_max, int use_dfl,
+                          float* loss_out, float* grad_pred_dist, float* grad_pred_bboxes, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (!pred_bboxes || !target_bboxes || !target_scores || !fg_mask || !target_scores_sum_d || !loss_out || !workspace ||
+        (use_dfl && (!pred_dist || !anchor_points))) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (B < 1 || A < 1 || nc < 1 || reg_max < 1 || reg_max > 63) { ycr_set_error("bad B/A/nc/reg_max"); return YCR_E_ARG; }
+    return launch_bbox_loss(pred_dist, pred_bboxes, anchor_points, target_bboxes, target_scores, fg_mask, target_scores_sum_d,
+                            B, A, nc, reg_max, use_dfl, loss_out, grad_pred_dist, grad_pred_bboxes, workspace,
+                            workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, void* stream) {

@@ -159,3 +159,53 @@ class v8SegmentationLoss:
         total, out = _SegLossFn.apply(self, gt, cand_cap, *feats)
         del keep
         return total, out[1:3].detach()
+
+
+class _BboxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_dist, pred_bboxes, anchor_points, target_bboxes, target_scores, tss, fg_mask, reg_max, use_dfl):
+        dev = pred_bboxes.device
+        lib = L.lib()
+        B, A = pred_bboxes.shape[:2]
+        nc = target_scores.shape[-1]
+        pd = pred_dist.float().contiguous()
+        pb = pred_bboxes.float().contiguous()
+        need = pred_dist.requires_grad or pred_bboxes.requires_grad
+        gd = torch.empty_like(pd) if need else None
+        gb = torch.empty_like(pb) if need else None
+        out = torch.empty(2, device=dev)
+        tss_t = torch.as_tensor(tss, dtype=torch.float32, device=dev).reshape(1).contiguous()
+        keep = [anchor_points.float().contiguous(), target_bboxes.float().contiguous(),
+                target_scores.float().contiguous(), fg_mask.to(torch.uint8).contiguous(), tss_t]
+        ws = L.Workspace.get("bbox_loss", lib.ycr_bbox_loss_workspace_bytes(B, A), dev)
+        rc = lib.ycr_bbox_loss_fwd_bwd(pd.data_ptr(), pb.data_ptr(), keep[0].data_ptr(), keep[1].data_ptr(),
+                                       keep[2].data_ptr(), keep[3].data_ptr(), keep[4].data_ptr(), B, A, nc,
+                                       int(reg_max), int(bool(use_dfl)), out.data_ptr(),
+                                       gd.data_ptr() if need else None, gb.data_ptr() if need else None,
+                                       ws.data_ptr(), ws.numel(), L.stream_ptr(dev))
+        L.check(rc, "ycr_bbox_loss_fwd_bwd")
+        ctx.gd, ctx.gb = gd, gb
+        return out[0].clone(), out[1].clone()
+
+    @staticmethod
+    def backward(ctx, g_iou, g_dfl):
+        # the kernel stored d(loss_iou)/d(pred_bboxes) and d(loss_dfl)/d(pred_dist); the two terms do not mix
+        gd = ctx.gd * g_dfl if ctx.gd is not None else None
+        gb = ctx.gb * g_iou if ctx.gb is not None else None
+        return gd, gb, None, None, None, None, None, None, None
+
+
+class BboxLoss(nn.Module):
+    """utils/loss.py:53-87 — CIoU + DFL box loss, same constructor and forward signature; returns
+    `(loss_iou, loss_dfl)`.  Not called by the live polar v8SegmentationLoss (utils/loss.py:211 constructs it
+    only); provided for the north_star's 'DFL/CIoU box terms' and the fork's `ori*` classes."""
+
+    def __init__(self, reg_max, use_dfl=False):
+        super().__init__()
+        self.reg_max = reg_max
+        self.use_dfl = use_dfl
+
+    def forward(self, pred_dist, pred_bboxes, anchor_points, target_bboxes, target_scores, target_scores_sum, fg_mask):
+        L.require_cuda(pred_dist, pred_bboxes, target_bboxes, target_scores, fg_mask)
+        return _BboxLossFn.apply(pred_dist, pred_bboxes, anchor_points, target_bboxes, target_scores,
+                                 target_scores_sum, fg_mask, self.reg_max, self.use_dfl)
