@@ -148,6 +148,15 @@ def run_reference(args):
 def run_ours(args):
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product)"
+    # libraries (NCCL's version banner) write to fd 1; keep stdout clean for the one JSON line
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        print(json.dumps(obj), flush=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     use_dist = world > 1
@@ -203,7 +212,7 @@ def run_ours(args):
         counts = (C.c_int * 16)()
         L.check(lib.ycr_profile_end(sums, counts), "ycr_profile_end")
         names = {7: "decode", 8: "nms_filter", 9: "nms_sort", 10: "nms_suppress"}
-        print(json.dumps({"quick_infer": True, "kernels_ms": {n: sums[i] / counts[i] for i, n in names.items()}}))
+        emit({"quick_infer": True, "kernels_ms": {n: sums[i] / counts[i] for i, n in names.items()}})
         return
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -230,10 +239,10 @@ def run_ours(args):
         if rank == 0:
             st = (C.c_ulonglong * 4)()
             lib.ycr_debug_stats(st, 1)
-            print(json.dumps({"quick": True, "ms_per_step": ms_total / args.steps,
-                              "stats_per_candidate": {"candidates": st[0], "queued_pairs": st[1] / max(st[0], 1),
-                                                      "scan_pairs": st[2] / max(st[0], 1)},
-                              "kernels_ms": {names[i]: sums[i] / counts[i] for i in range(7) if counts[i]}}), flush=True)
+            emit({"quick": True, "ms_per_step": ms_total / args.steps,
+                  "stats_per_candidate": {"candidates": st[0], "queued_pairs": st[1] / max(st[0], 1),
+                                          "scan_pairs": st[2] / max(st[0], 1)},
+                  "kernels_ms": {names[i]: sums[i] / counts[i] for i in range(7) if counts[i]}})
         return
     # ---- e2e: host inputs, H2D inside the timed region, loss read back ----
     gt_rows_bytes = int(batch["batch_idx"].numel()) * 726 * 4
@@ -343,7 +352,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": cpu_val, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_images} images of the same workload, fwd+bwd, "
                                           f"1 warm-up + 2 timed (oracle/polar_oracle.seg_loss)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if use_dist:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -44,8 +44,8 @@ def test_validator_postprocess_and_metrics():
         assert cb.shape == (p.shape[0], 10) and cm.shape == (p.shape[0], 10)
         assert not bool(cm.any())                      # masks are all-zero in the reference snapshot
         assert torch.equal(conf, p[:, 4]) and tcls.numel() == cfg.gts
-        # correctness at IoU 0.5 implies a same-class GT box with IoU >= 0.5, and is monotone in the threshold
-        assert bool((cb[:, 1:].int() <= cb[:, :-1].int()).all())
+        # at most one detection is matched to a GT per threshold (utils matching is one-to-one)
+        assert int(cb[:, 0].sum()) <= cfg.gts and int(cb[:, -1].sum()) <= int(cb[:, 0].sum())
     # every image has at least one near-GT anchor predicted with the right class in this synthetic set-up
     assert sum(int(s[0][:, 0].sum()) for s in val.stats) > 0
 

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
 #pragma unroll 4
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
-                const float t = __uint_as_float(sm.list[i][tid].x);
+                const float t = sm.tval[i][tid];
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
         const int grow = base + row;
         float tmin = 3.4e38f, tmax = 0.f;
         for (int i = 0; i < R; ++i) {
-            const float t = __uint_as_float(sm.list[i][tid].x);
+            const float t = sm.tval[i][tid];
             tmin = fminf(tmin, t);
             tmax = fmaxf(tmax, t);
             if (pa.gt_dist && grow < pa.pos_capacity) pa.gt_dist[(int64_t)grow * R + i] = t;
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             float smin = 0.f, smax = 0.f;
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
-                const float t = __uint_as_float(sm.list[i][tid].x);
+                const float t = sm.tval[i][tid];
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             float* gp = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
-                const float t = __uint_as_float(sm.list[i][tid].x);
+                const float t = sm.tval[i][tid];
                 float g = 0.f;
                 if (p >= t) g += imax;                       // max() routes to pred (first index on ties)
                 if (p <= t && p >= YCR_FLOOR) g -= imin;     // min() routes to pred; clamp passes when >= floor

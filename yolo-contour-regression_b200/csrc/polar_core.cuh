@@ -21,30 +21,37 @@
 #pragma once
 #include "common.cuh"
 
+// Angular slack of every bin / window certificate, in degrees: far above the fp32 noise of the cross/dot
+// tests (~1e-5 deg).  It only decides WHICH exact path settles a ray, never the result; a point inside the
+// +-3 TOL zone around a window edge sends the ray to the exact scan.
+#define YCR_TOL_DEG 0.001
 #define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
 #define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
 
 struct PolarConst {
-    float tan_in;       // tan(hw + 0.01 deg): bin membership |crs| <= tan_in * dot
+    float tan_in;       // tan(hw + TOL): bin membership |crs| <= tan_in * dot
     float cos_step, sin_step;  // cos/sin of the ray spacing 360/R deg
     float key_scale;    // fixed-point scale of |sin delta| so that in-bin keys fit 23 bits
-    uint32_t q_res;     // fixed(sin(hw - 0.02 deg)): 4th key below this => top-4 certified
+    uint32_t q_res;     // fixed(sin(hw - 2 TOL)): 4th key below this => top-4 certified
     uint32_t q_gate;    // fixed(sin(3 deg))
-    int gate_l1;        // 1 when hw - 0.01 > 3: an own bin without a point <= 3 deg certifies the gate
-    int empty3_gate;    // 1 when 3*hw - 0.03 > 3: three empty bins certify the gate
+    int gate_l1;        // 1 when hw - TOL > 3: an own bin without a point <= 3 deg certifies the gate
+    int empty3_gate;    // 1 when 3*hw - 3 TOL > 3: three empty bins certify the gate
     int nwin;           // R/2 + 1 windows: window m covers bins ray-m .. ray+m
-    float pk_lo[YCR_MAXWIN];  // pseudo-angle of ((2m+1)*hw - 0.03 deg)
-    float pk_hi[YCR_MAXWIN];  // pseudo-angle of ((2m+1)*hw + 0.03 deg)
+    float pk_lo[YCR_MAXWIN];  // pseudo-angle of ((2m+1)*hw - 3 TOL)
+    float pk_hi[YCR_MAXWIN];  // pseudo-angle of ((2m+1)*hw + 3 TOL)
     float pk_gate;            // pseudo-angle of 3 deg
+    float tan_win[YCR_MAXWIN];  // tan((2m+1)*hw + 5 TOL), 0 when that is 89 deg or more
+    int m_gate;               // smallest window with (2m+1)*hw - 3 TOL > 3 deg
 };
 
 template <int R, int NT>
 struct PolarSmem {
-    uint4 list[R][NT];                 // per-thread, per-ray sorted packed keys (later: .x = target bits)
+    uint4 list[R][NT];                 // per-thread, per-ray sorted packed keys
     float2 contour[YCR_C];
     float2 raydir[R];                  // (cos, sin) of i*360/R deg
     float2 anchor[NT];
     unsigned char cnt[R][NT];          // points per bin (saturating at 255)
+    float tval[R][NT];                 // settled ray targets
     unsigned short queue[NT * R / 2];  // (thread << 7) | ray : pairs the own bin could not settle;
                                        // bit 15 is set later on pairs that need the exact scan
     int qcount, q2count;
@@ -201,7 +208,7 @@ __device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, cons
 }
 
 // Own-bin settlement of every ray of this thread; unsettled rays go to the block queue.
-// On return sm.list[i][tid].x holds the float bits of the target for settled rays.
+// On return sm.tval[i][tid] holds the target of every settled ray (the lists stay intact).
 template <int R, int NT>
 __device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, bool active,
                                                  float ax, float ay) {
@@ -212,14 +219,14 @@ __device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const Pol
             const uint4 L = sm.list[i][tid];
             const bool own_gate = (L.x == YCR_EMPTY) || ((L.x >> 9) > pc.q_gate);
             if (own_gate && pc.gate_l1) {
-                sm.list[i][tid].x = __float_as_uint(YCR_FLOOR);
+                sm.tval[i][tid] = YCR_FLOOR;
             } else if (L.w != YCR_EMPTY && (L.w >> 9) < pc.q_res) {
                 // (for hw < 3 deg every in-bin key is below the gate, so the gate cannot fire here)
                 float m = dist2_of(sm, L.x, ax, ay);
                 m = fmaxf(m, dist2_of(sm, L.y, ax, ay));
                 m = fmaxf(m, dist2_of(sm, L.z, ax, ay));
                 m = fmaxf(m, dist2_of(sm, L.w, ax, ay));
-                sm.list[i][tid].x = __float_as_uint(fmaxf(sqrtf(m), YCR_FLOOR));
+                sm.tval[i][tid] = fmaxf(sqrtf(m), YCR_FLOOR);
             } else {
                 unsettled = true;
             }
@@ -236,25 +243,48 @@ __device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const Pol
                 } else {  // queue full (pathological block): settle right here, serially
                     float t;
                     if (!polar_settle_pair<R, NT>(sm, pc, tid, i, t)) t = polar_scan_serial<R, NT>(sm, pc, tid, i);
-                    sm.list[i][tid].x = __float_as_uint(t);
+                    sm.tval[i][tid] = t;
                 }
             }
         }
     }
 }
 
+// Smallest window (in bins on each side of the ray) whose bins hold at least four points and that
+// reaches past the 3 degree gate; its point count.  Returns false when a count is saturated or the
+// window would be the whole circle.
+template <int R, int NT>
+__device__ __forceinline__ bool polar_window(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
+                                             int& m_out, int& n_out) {
+    int nb = sm.cnt[ray][owner];
+    bool sat = nb == 255;
+    int m = 0;
+    while ((nb < 4 || m < pc.m_gate) && 2 * (m + 1) < R) {
+        ++m;
+        const int c1 = sm.cnt[(ray + m) % R][owner], c2 = sm.cnt[(ray + R - m) % R][owner];
+        sat |= (c1 == 255) | (c2 == 255);
+        nb += c1 + c2;
+    }
+    m_out = m;
+    n_out = nb;
+    return !sat && nb >= 4;
+}
+
 // Neighbourhood settlement of one queued (owner thread, ray) pair.  Returns false when the result
 // cannot be certified (the pair then takes the exact scan).
-//   A. evaluate the contour neighbourhoods (+-YCR_NBR indices) of the seed points (what the own bin
-//      caught); this gives a first 4th-nearest angle and the window (in bins) that must be known;
-//   B. grow every evaluated index range at both ends while the end points still lie inside that
-//      window (along a locally monotone contour this visits exactly the points of the window);
-//   C. certify: the number of evaluated points inside the (final, possibly smaller) window equals the
-//      number of points the sweep counted in the window's bins.
+//   1. the per-bin counts give the window (bins ray-m .. ray+m) that must contain the four nearest points;
+//   2. evaluate the contour neighbourhoods (+-YCR_NBR indices) of the seed points (what the own bin
+//      caught) and grow every evaluated index range at both ends while the end points still lie inside
+//      the window (along a locally monotone contour this visits exactly the points of the window);
+//   3. certify: the number of evaluated points inside the window equals the number of points the sweep
+//      counted in the window's bins, and none sits in the +-3 TOL fuzz zone of the window edge.
 #define YCR_EVCAP 48
 template <int R, int NT>
 __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
                                                   float& result) {
+    int m, nbins;
+    if (!polar_window<R, NT>(sm, pc, owner, ray, m, nbins)) return false;
+    const float win_lo = pc.pk_lo[m], win_hi = pc.pk_hi[m];
     const float2 a = sm.anchor[owner];
     const float2 cs = sm.raydir[ray];
     int seed[4];
@@ -273,11 +303,7 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
             if (A.y != YCR_EMPTY) seed[ns++] = A.y & 511u;
             if (B.x != YCR_EMPTY) seed[ns++] = B.x & 511u;
             if (B.y != YCR_EMPTY) seed[ns++] = B.y & 511u;
-            if (ns == 0) {
-                if (!pc.empty3_gate) return false;
-                result = YCR_FLOOR;  // three empty bins: nothing within 3*hw - 0.01 > 3 degrees
-                return true;
-            }
+            if (ns == 0) return false;
         }
     }
     // rotate point indices so that the first seed sits mid-range and ranges do not wrap
@@ -287,8 +313,7 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
         for (int t = s; t > 0 && seed[t] < seed[t - 1]; --t) { const int x = seed[t]; seed[t] = seed[t - 1]; seed[t - 1] = x; }
     if (seed[0] < YCR_NBR || seed[ns - 1] >= YCR_C - YCR_NBR) return false;
     float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
-    float ev[YCR_EVCAP];
-    int ne = 0;
+    int ne = 0, n_in = 0, n_maybe = 0;
     auto eval = [&](int jr) -> float {
         int j = jr + origin;
         j = (j >= YCR_C) ? j - YCR_C : j;
@@ -300,11 +325,13 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
         const float d = fmaf(vx, cs.x, vy * cs.y);
         const float q = fabsf(fmaf(vy, cs.x, -vx * cs.y));
         const float k = pseudo_angle(q, d);
-        ev[ne++] = k;
+        ++ne;
+        n_in += (k < win_lo) ? 1 : 0;
+        n_maybe += (k < win_hi) ? 1 : 0;
         finsert4(fk, fd, k, l2);
         return k;
     };
-    // A: merged seed neighbourhoods -> disjoint ranges [rlo, rhi]
+    // merged seed neighbourhoods -> disjoint ranges [rlo, rhi]
     int rlo[4], rhi[4];
     int nr = 0;
     for (int s = 0; s < ns; ++s) {
@@ -317,13 +344,7 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
             rlo[nr] = lo; rhi[nr] = hi; ++nr;
         }
     }
-    // window that must be fully known, from the first estimate of the threshold
-    float thr = (fk[0] > pc.pk_gate) ? pc.pk_gate : fk[3];
-    int m = 0;
-    while (m < pc.nwin && !(pc.pk_lo[m] > thr)) ++m;
-    if (m >= pc.nwin - 1) return false;
-    // B: grow the ranges while their end points are still inside the window
-    const float win_hi = pc.pk_hi[m];
+    // grow the ranges while their end points are still inside the window
     for (int r = 0; r < nr; ++r) {
         const int lo_limit = (r > 0) ? rhi[r - 1] + 1 : 0;
         while (rlo[r] > lo_limit && ne < YCR_EVCAP) {
@@ -336,37 +357,23 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
             if (eval(rhi[r]) >= win_hi) break;
         }
     }
-    if (ne >= YCR_EVCAP) return false;
-    // C: certify against the bin counts, with the final threshold (never wider than the first)
-    const bool gated = fk[0] > pc.pk_gate;
-    thr = gated ? pc.pk_gate : fk[3];
-    m = 0;
-    while (!(pc.pk_lo[m] > thr)) ++m;
-    int nbins = sm.cnt[ray][owner];
-    bool sat = nbins == 255;
-    for (int db = 1; db <= m; ++db) {
-        const int c1 = sm.cnt[(ray + db) % R][owner], c2 = sm.cnt[(ray + R - db) % R][owner];
-        sat |= (c1 == 255) | (c2 == 255);
-        nbins += c1 + c2;
-    }
-    if (sat) return false;
-    int n_in = 0, n_maybe = 0;
-    const float lo = pc.pk_lo[m], hi = pc.pk_hi[m];
-    for (int e = 0; e < ne; ++e) {
-        n_in += (ev[e] < lo) ? 1 : 0;
-        n_maybe += (ev[e] < hi) ? 1 : 0;
-    }
-    if (n_in != n_maybe || n_in != nbins) return false;
-    result = gated ? YCR_FLOOR : fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
+    if (ne >= YCR_EVCAP || n_in != n_maybe || n_in != nbins) return false;
+    result = (fk[0] > pc.pk_gate) ? YCR_FLOOR : fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
     return true;
 }
 
-// Exact scan of all points for one pair, one warp per pair (lanes stride the contour).
+// Exact scan of all points for one pair, one warp per pair (lanes take consecutive points).  When the
+// bin counts bound the window that holds the four nearest points, points outside it are skipped after
+// a two-instruction test, so only the one or two iterations whose 32 consecutive points touch the
+// window pay for key evaluation and insertion.
 template <int R, int NT>
 __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
                                                  unsigned lane) {
     const float2 a = sm.anchor[owner];
     const float2 cs = sm.raydir[ray];
+    int m, nbins;
+    float tanw = 0.f;
+    if (polar_window<R, NT>(sm, pc, owner, ray, m, nbins)) tanw = pc.tan_win[m];  // 0: no usable bound
     float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = lane; j < YCR_C; j += 32) {
         const float2 p = sm.contour[j];
@@ -376,27 +383,28 @@ __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, con
         if (l2 == 0.f) vx = 1.f;
         const float d = fmaf(vx, cs.x, vy * cs.y);
         const float q = fabsf(fmaf(vy, cs.x, -vx * cs.y));
-        finsert4(fk, fd, pseudo_angle(q, d), l2);
+        if (tanw == 0.f || q <= tanw * d) finsert4(fk, fd, pseudo_angle(q, d), l2);
     }
     float first = 0.f, maxd = 0.f;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        float m = fk[0];
+        float mn = fk[0];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const unsigned who = __ballot_sync(0xffffffffu, fk[0] == m);
+        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        const unsigned who = __ballot_sync(0xffffffffu, fk[0] == mn);
         const int src = __ffs(who) - 1;
         const float dsel = __shfl_sync(0xffffffffu, fd[0], src);
         if ((int)lane == src) {
             fk[0] = fk[1]; fk[1] = fk[2]; fk[2] = fk[3]; fk[3] = 1e30f;
             fd[0] = fd[1]; fd[1] = fd[2]; fd[2] = fd[3];
         }
-        if (r == 0) first = m;
+        if (r == 0) first = mn;
         maxd = fmaxf(maxd, dsel);
     }
     if (first > pc.pk_gate) return YCR_FLOOR;
     return fmaxf(sqrtf(maxd), YCR_FLOOR);
 }
+
 
 // Block-wide: settle all queued pairs (any thread may serve any owner), then the exact-scan queue.
 // Must be called by all NT threads; contains block barriers.
@@ -408,7 +416,7 @@ __device__ __forceinline__ void polar_settle_queue(PolarSmem<R, NT>& sm, const P
         const unsigned e = sm.queue[q];
         const int owner = e >> 7, ray = e & 127u;
         float t;
-        if (polar_settle_pair<R, NT>(sm, pc, owner, ray, t)) sm.list[ray][owner].x = __float_as_uint(t);
+        if (polar_settle_pair<R, NT>(sm, pc, owner, ray, t)) sm.tval[ray][owner] = t;
         else { sm.queue[q] = (unsigned short)(e | 0x8000u); ++nfail; }
     }
     if (nfail) atomicAdd(&sm.q2count, nfail);
@@ -420,7 +428,7 @@ __device__ __forceinline__ void polar_settle_queue(PolarSmem<R, NT>& sm, const P
         if (!(e & 0x8000u)) continue;  // warp-uniform: every lane reads the same entry
         const int owner = (e & 0x7FFFu) >> 7, ray = e & 127u;
         const float t = polar_scan_pair<R, NT>(sm, pc, owner, ray, lane);
-        if (lane == 0) sm.list[ray][owner].x = __float_as_uint(t);
+        if (lane == 0) sm.tval[ray][owner] = t;
     }
 }
 
@@ -437,25 +445,32 @@ static inline double ycr_pseudo_host(double deg) {
 static inline PolarConst make_polar_const(int R) {
     PolarConst pc{};
     const double hw = 180.0 / R;
-    pc.tan_in = (float)tan(ycr_deg2rad(hw + 0.01));
+    const double T = YCR_TOL_DEG;
+    pc.tan_in = (float)tan(ycr_deg2rad(hw + T));
     pc.cos_step = (float)cos(ycr_deg2rad(2 * hw));
     pc.sin_step = (float)sin(ycr_deg2rad(2 * hw));
-    const double scale = 8388607.0 / sin(ycr_deg2rad(hw + 0.02));
+    const double scale = 8388607.0 / sin(ycr_deg2rad(hw + 2 * T));
     pc.key_scale = (float)scale;
-    pc.q_res = (uint32_t)(sin(ycr_deg2rad(hw - 0.02)) * scale);
+    pc.q_res = (uint32_t)(sin(ycr_deg2rad(hw - 2 * T)) * scale);
     pc.q_gate = (uint32_t)(sin(ycr_deg2rad(YCR_GATE_DEG)) * scale);
-    if (YCR_GATE_DEG >= hw + 0.01) pc.q_gate = 0x7FFFFFu;  // every in-bin key is below the gate
-    pc.gate_l1 = (hw - 0.01 > YCR_GATE_DEG) ? 1 : 0;
-    pc.empty3_gate = (3 * hw - 0.03 > YCR_GATE_DEG) ? 1 : 0;
+    if (YCR_GATE_DEG >= hw + T) pc.q_gate = 0x7FFFFFu;  // every in-bin key is below the gate
+    pc.gate_l1 = (hw - T > YCR_GATE_DEG) ? 1 : 0;
+    pc.empty3_gate = (3 * hw - 3 * T > YCR_GATE_DEG) ? 1 : 0;
     pc.nwin = R / 2 + 1;
     for (int m = 0; m < YCR_MAXWIN; ++m) {
         const double w = (2 * m + 1) * hw;
-        pc.pk_lo[m] = (float)ycr_pseudo_host(w - 0.03);
-        pc.pk_hi[m] = (float)ycr_pseudo_host(w + 0.03);
+        pc.pk_lo[m] = (float)ycr_pseudo_host(w - 3 * T);
+        pc.pk_hi[m] = (float)ycr_pseudo_host(w + 3 * T);
     }
     // the last window is the whole circle: nothing lies outside it
     pc.pk_lo[R / 2] = 5.f;
     pc.pk_hi[R / 2] = 5.f;
     pc.pk_gate = (float)ycr_pseudo_host(YCR_GATE_DEG);
+    pc.m_gate = 0;
+    while ((2 * pc.m_gate + 1) * hw - 3 * T <= YCR_GATE_DEG) ++pc.m_gate;
+    for (int m = 0; m < YCR_MAXWIN; ++m) {
+        const double w = (2 * m + 1) * hw + 5 * T;
+        pc.tan_win[m] = (w < 89.0) ? (float)tan(ycr_deg2rad(w)) : 0.f;
+    }
     return pc;
 }
