@@ -273,12 +273,13 @@ __device__ __forceinline__ bool polar_window(const PolarSmem<R, NT>& sm, const P
 // Neighbourhood settlement of one queued (owner thread, ray) pair.  Returns false when the result
 // cannot be certified (the pair then takes the exact scan).
 //   1. the per-bin counts give the window (bins ray-m .. ray+m) that must contain the four nearest points;
-//   2. evaluate the contour neighbourhoods (+-YCR_NBR indices) of the seed points (what the own bin
-//      caught) and grow every evaluated index range at both ends while the end points still lie inside
-//      the window (along a locally monotone contour this visits exactly the points of the window);
+//   2. the points the own bin caught are normally consecutive contour indices: evaluate that index range
+//      widened by YCR_NBR on both sides, then keep growing either end while its last point still lies
+//      inside the window (along a locally monotone contour this visits exactly the points of the window);
 //   3. certify: the number of evaluated points inside the window equals the number of points the sweep
 //      counted in the window's bins, and none sits in the +-3 TOL fuzz zone of the window edge.
-#define YCR_EVCAP 48
+// Seeds spread over distant parts of the contour (several arcs through one bin) go to the exact scan.
+#define YCR_GROW 20
 template <int R, int NT>
 __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
                                                   float& result) {
@@ -287,77 +288,57 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
     const float win_lo = pc.pk_lo[m], win_hi = pc.pk_hi[m];
     const float2 a = sm.anchor[owner];
     const float2 cs = sm.raydir[ray];
-    int seed[4];
-    int ns = 0;
+    uint4 L = sm.list[ray][owner];
+    if (L.x == YCR_EMPTY) {  // empty own bin (only reachable when hw < 3 deg): nearest of each neighbour bin
+        L.x = sm.list[(ray + R - 1) % R][owner].x;
+        L.y = sm.list[(ray + 1) % R][owner].x;
+        if (L.x == YCR_EMPTY) { L.x = L.y; L.y = YCR_EMPTY; }
+        if (L.x == YCR_EMPTY) return false;
+    }
+    // index range of the seeds on the circle of contour indices, measured from the first seed
+    const int j0 = L.x & 511u;
+    int dmin = 0, dmax = 0;
     {
-        const uint4 L = sm.list[ray][owner];
-        if (L.x != YCR_EMPTY) {
-            seed[ns++] = L.x & 511u;
-            if (L.y != YCR_EMPTY) seed[ns++] = L.y & 511u;
-            if (L.z != YCR_EMPTY) seed[ns++] = L.z & 511u;
-            if (L.w != YCR_EMPTY) seed[ns++] = L.w & 511u;
-        } else {  // empty own bin (only reachable when hw < 3 deg): nearest two of each neighbour bin
-            const uint4 A = sm.list[(ray + R - 1) % R][owner];
-            const uint4 B = sm.list[(ray + 1) % R][owner];
-            if (A.x != YCR_EMPTY) seed[ns++] = A.x & 511u;
-            if (A.y != YCR_EMPTY) seed[ns++] = A.y & 511u;
-            if (B.x != YCR_EMPTY) seed[ns++] = B.x & 511u;
-            if (B.y != YCR_EMPTY) seed[ns++] = B.y & 511u;
-            if (ns == 0) return false;
+        const uint32_t e[3] = {L.y, L.z, L.w};
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+            if (e[s] != YCR_EMPTY) {
+                int d = (int)(e[s] & 511u) - j0;
+                d = (d > YCR_C / 2) ? d - YCR_C : ((d < -YCR_C / 2) ? d + YCR_C : d);
+                dmin = min(dmin, d);
+                dmax = max(dmax, d);
+            }
         }
     }
-    // rotate point indices so that the first seed sits mid-range and ranges do not wrap
-    const int origin = (seed[0] + YCR_C / 2) % YCR_C;
-    for (int s = 0; s < ns; ++s) seed[s] = (seed[s] - origin + YCR_C) % YCR_C;
-    for (int s = 1; s < ns; ++s)  // insertion sort, ns <= 4
-        for (int t = s; t > 0 && seed[t] < seed[t - 1]; --t) { const int x = seed[t]; seed[t] = seed[t - 1]; seed[t - 1] = x; }
-    if (seed[0] < YCR_NBR || seed[ns - 1] >= YCR_C - YCR_NBR) return false;
+    if (dmax - dmin > 16) return false;
     float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
-    int ne = 0, n_in = 0, n_maybe = 0;
-    auto eval = [&](int jr) -> float {
-        int j = jr + origin;
-        j = (j >= YCR_C) ? j - YCR_C : j;
+    int n_in = 0, n_maybe = 0;
+    auto eval = [&](int d) -> float {  // contour point j0 + d (mod C)
+        int j = j0 + d;
+        j = (j < 0) ? j + YCR_C : ((j >= YCR_C) ? j - YCR_C : j);
         const float2 p = sm.contour[j];
         float vx = p.x - a.x;
         const float vy = p.y - a.y;
         const float l2 = fmaf(vx, vx, vy * vy);
         if (l2 == 0.f) vx = 1.f;
-        const float d = fmaf(vx, cs.x, vy * cs.y);
-        const float q = fabsf(fmaf(vy, cs.x, -vx * cs.y));
-        const float k = pseudo_angle(q, d);
-        ++ne;
+        const float k = pseudo_angle(fabsf(fmaf(vy, cs.x, -vx * cs.y)), fmaf(vx, cs.x, vy * cs.y));
         n_in += (k < win_lo) ? 1 : 0;
         n_maybe += (k < win_hi) ? 1 : 0;
         finsert4(fk, fd, k, l2);
         return k;
     };
-    // merged seed neighbourhoods -> disjoint ranges [rlo, rhi]
-    int rlo[4], rhi[4];
-    int nr = 0;
-    for (int s = 0; s < ns; ++s) {
-        const int lo = seed[s] - YCR_NBR, hi = seed[s] + YCR_NBR;
-        if (nr > 0 && lo <= rhi[nr - 1] + 1) {
-            for (int jr = rhi[nr - 1] + 1; jr <= hi; ++jr) eval(jr);
-            rhi[nr - 1] = max(rhi[nr - 1], hi);
-        } else {
-            for (int jr = lo; jr <= hi; ++jr) eval(jr);
-            rlo[nr] = lo; rhi[nr] = hi; ++nr;
-        }
+    int lo = dmin - YCR_NBR, hi = dmax + YCR_NBR;
+    float klo = 0.f, khi = 0.f;
+    for (int d = lo; d <= hi; ++d) {
+        const float k = eval(d);
+        if (d == lo) klo = k;
+        khi = k;
     }
-    // grow the ranges while their end points are still inside the window
-    for (int r = 0; r < nr; ++r) {
-        const int lo_limit = (r > 0) ? rhi[r - 1] + 1 : 0;
-        while (rlo[r] > lo_limit && ne < YCR_EVCAP) {
-            --rlo[r];
-            if (eval(rlo[r]) >= win_hi) break;
-        }
-        const int hi_limit = (r + 1 < nr) ? rlo[r + 1] - 1 : YCR_C - 1;
-        while (rhi[r] < hi_limit && ne < YCR_EVCAP) {
-            ++rhi[r];
-            if (eval(rhi[r]) >= win_hi) break;
-        }
-    }
-    if (ne >= YCR_EVCAP || n_in != n_maybe || n_in != nbins) return false;
+    int g = 0;
+    while (klo < win_hi && g < YCR_GROW) { klo = eval(--lo); ++g; }
+    int h = 0;
+    while (khi < win_hi && h < YCR_GROW) { khi = eval(++hi); ++h; }
+    if (g >= YCR_GROW || h >= YCR_GROW || n_in != n_maybe || n_in != nbins) return false;
     result = (fk[0] > pc.pk_gate) ? YCR_FLOOR : fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
     return true;
 }
