@@ -305,6 +305,12 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peaks()
+    traffic = {}
+    try:
+        tf = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tf[-1]))) if tf else {}
+    except Exception:
+        pass
     ms_step = ms_total / args.steps
     value = world * B / (ms_step / 1e3)
     e2e_val = world * B / (ms_e2e / e_steps / 1e3)
@@ -332,7 +338,8 @@ def run_ours(args):
                    "l2": f"inputs per step {in_bytes / 1e6:.0f} MB + grads of the same size > 126 MB L2",
                    "parallelism": f"dp{world}, no data-path collective"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": dom_gbs / peak, "traffic": traffic.get(dom) if args.workload == "C2" else None,
+                     "peak_source": peak_src,
                      "note": "algorithmic bytes of the whole path (SURVEY 8-d: %.2f MB/img) / avg duration of the "
                              "dominant kernel; see roofline_step and kernels_ms" % (bytes_img / 1e6)},
         "roofline_step": {"achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
@@ -341,7 +348,7 @@ def run_ours(args):
         "loss_stream_hbm_frac": (stream_bytes / (kern["loss_stream"] * 1e-3) / 1e9 / peak) if "loss_stream" in kern else None,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": in_bytes + gt_rows_bytes,
                 "d2h_bytes_per_step": 4, "steps": e_steps},
-        "gpu_launches": int(sum(counts[i] for i in range(7)) + 3 * args.steps),
+        "gpu_launches": int(sum(counts[i] for i in range(7)) + 4 * args.steps),  # + k_finalize_counts, 3x k_scale
         "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
                   "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",
                   "ms_per_step": ms_inf / i_steps, "kernels_ms": ikern,
