@@ -294,3 +294,20 @@ def test_pack_targets_kernel_matches_oracle():
     m = po.in_box_mask((po.make_anchors(cfg.level_shapes, cfg.strides)[0] * po.make_anchors(cfg.level_shapes, cfg.strides)[1]),
                        ref[..., 1:5])
     assert int(m.sum()) <= cap                                       # host bound really is an upper bound
+
+
+def test_capacity_overflow_is_loud():
+    """A workspace sized for too few candidates must not produce a plausible-looking loss."""
+    from ycr_b200.loss import v8SegmentationLoss
+    from ycr_b200 import synth
+    dev = _dev()
+    cfg = synth.PathConfig("o", 2, 4, 160, nc=10)
+    batch = synth.make_gts(cfg, 11)
+    feats = [f.to(dev) for f in synth.make_feats(cfg, 11)]
+    crit = v8SegmentationLoss(nc=cfg.nc, nm=cfg.rays, strides=cfg.strides, device=dev)
+    crit._shapes = cfg.level_shapes
+    packed, cap = crit.pack_targets(batch, cfg.batch, (160, 160))
+    total, items = crit.call_packed(feats, packed, cap)
+    assert torch.isfinite(total)
+    total, items = crit.call_packed(feats, packed, 8)
+    assert torch.isnan(total) and bool(torch.isnan(items).all())

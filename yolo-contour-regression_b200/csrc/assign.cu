@@ -427,7 +427,7 @@ __global__ void k_finalize_counts(AssignWs ws, int B, int* img_base, float* tss,
         img_base[B] = run;
         tss[0] = fmaxf((float)s, 1.f);
         tss[1] = (float)s;
-        if (n_pos_d) *n_pos_d = run;
+        if (n_pos_d) *n_pos_d = ws.err[0] ? -1 : run;  // -1: candidate capacity exceeded, nothing was assigned
     }
 }
 

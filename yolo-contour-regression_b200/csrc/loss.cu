@@ -186,6 +186,10 @@ __global__ void __launch_bounds__(1024) k_loss_finalize(AssignWs ws, int B, int 
         loss_out[1] = l_box;
         loss_out[2] = l_cls;
         loss_out[3] = (float)tss;
+        if (ws.err[0]) {  // candidate capacity exceeded: the assignment was skipped - fail loudly, not silently
+            const float nan = __int_as_float(0x7fc00000);
+            loss_out[0] = loss_out[1] = loss_out[2] = nan;
+        }
     }
 }
 

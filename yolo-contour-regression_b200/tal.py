@@ -167,6 +167,8 @@ class TaskAlignedAssigner(nn.Module):
                             ws.numel(), cap, L.stream_ptr(dev))
         L.check(rc, "ycr_assign")
         P = int(o["npos"].item())
+        if P < 0:
+            raise L.YcrError("ycr_assign: candidate capacity exceeded (workspace sized for too few candidates)")
         if self.debug_metrics:
             self.last_overlaps, self.last_align_metric = o["overlaps"], o["align"]
         del keep
