@@ -1,3 +1,5 @@
+"""Aggregate an `ncu --page source --print-source cuda,sass --csv` dump per CUDA source line:
+stall samples, executed instructions and average active threads.  usage: ncu_lines.py dump.csv [top_n]"""
 import csv,sys
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=None; cur_file=None

@@ -100,7 +100,7 @@ class v8SegmentationLoss:
         self.use_dfl = self.reg_max > 1
         self.assigner = TaskAlignedAssigner(topk=10, num_classes=self.nc, alpha=0.5, beta=4.0)  # utils/loss.py:210
         self.polar_loss = MaskIOULoss()
-        self.rays = 36 if self.nm == 36 else int(self.nm)  # utils/loss.py:818 keeps the first 36 channels
+        self.rays = int(self.nm)  # the reference keeps the first 36 of nm channels (utils/loss.py:818); here nm == rays
         self.acfg = L.AssignCfg(10, int(self.nc), int(self.rays), 0.5, 4.0, 1e-9)
         self.lcfg = L.LossCfg(float(box), float(cls))
 
