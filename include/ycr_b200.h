@@ -163,6 +163,12 @@ int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* g
 int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,
                      float* out_packed, void* stream);
 
+/* Contour resampling, replaces ops.resample_segments (utils/ops.py:676-693; n = 360 at
+ * utils/instance.py:202): S open polygons stored back to back in pts (total,2); polygon s owns rows
+ * offsets[s] .. offsets[s+1]-1.  Each is closed and linearly resampled to n_out points ->
+ * out (S, n_out, 2) float32, bit-identical to numpy's double-precision np.interp result. */
+int ycr_resample_segments(const float* pts, const int* offsets, int S, int n_out, float* out, void* stream);
+
 /* Box terms kept for API coverage (dormant on the live polar path): replaces BboxLoss.forward
  * (utils/loss.py:61-75) with _df_loss (:77-87), bbox_iou(CIoU) (utils/metrics.py:77-130) and bbox2dist
  * (utils/tal.py:1437-1440), forward and gradient in one pass.

@@ -509,3 +509,19 @@ def bbox_loss(pred_dist, pred_bboxes, anchor_points, target_bboxes, target_score
                ce(pd, tr.view(-1), reduction="none").view(tl.shape) * wr).mean(-1, keepdim=True)
         loss_dfl = (dfl * weight).sum() / target_scores_sum
     return loss_iou, loss_dfl
+
+
+# --------------------------------------------------------------------------------------------
+# contour resampling (data-format step in front of the path)
+# --------------------------------------------------------------------------------------------
+def resample_segments(segments, n: int = 360):
+    """utils/ops.py:676-693 resample_segments: close each (m,2) polygon, np.interp x and y onto
+    linspace(0, m, n) (double precision), return float32 (n,2) arrays."""
+    out = []
+    for s in segments:
+        s = np.asarray(s)
+        s = np.concatenate((s, s[0:1, :]), axis=0)
+        x = np.linspace(0, len(s) - 1, n)
+        xp = np.arange(len(s))
+        out.append(np.concatenate([np.interp(x, xp, s[:, i]) for i in range(2)], dtype=np.float32).reshape(2, -1).T)
+    return out

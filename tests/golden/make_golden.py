@@ -205,6 +205,14 @@ def main():
                         grad_bboxes=pb.grad.numpy(), gains=np.array([7.5, 1.5], np.float32))
     print("bbox_loss", float(li), float(ld), int(fg.sum()), flush=True)
 
+    # ---------------- contour resampling (utils/ops.py:676-693), ragged polygons ----------------
+    rng = np.random.default_rng(7)
+    polys = [rng.uniform(0, 1, size=(int(m), 2)).astype(np.float32) for m in (3, 4, 7, 16, 33, 100, 359, 360, 361, 500)]
+    res = rops.resample_segments([p.copy() for p in polys], n=360)
+    np.savez_compressed(os.path.join(HERE, "resample.npz"), sizes=np.array([len(p) for p in polys]),
+                        points=np.concatenate(polys), out=np.stack(res))
+    print("resample", len(polys), res[0].dtype, flush=True)
+
     # ---------------- inference path ----------------
     infer_cases = [
         ("infer_s160", synth.PathConfig("s160", 2, 0, 160, nc=10), 21, True),

@@ -34,6 +34,7 @@ void ycr_prof_mark(int tag, int end, cudaStream_t st) {
 }
 
 int debug_stats(unsigned long long* out_h, int reset);
+int launch_resample(const float* pts, const int* offsets, int S, int n_out, float* out, cudaStream_t st);
 size_t bbox_loss_workspace_bytes(int B, int A);
 int launch_bbox_loss(const float* pred_dist, const float* pred_bboxes, const float* anchor_points,
                      const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* tss_d,
@@ -191,6 +192,11 @@ int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int
     if (B < 1 || G < 0 || row_stride < 6 + 2 * YCR_C) { ycr_set_error("bad B/G/row_stride"); return YCR_E_ARG; }
     if (G == 0) return YCR_OK;
     return launch_pack_targets(targets, row_stride, N, B, G, img_w, img_h, out_packed, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ycr_resample_segments(const float* pts, const int* offsets, int S, int n_out, float* out, void* stream) {
+    if (S < 0 || n_out < 2 || (S > 0 && (!pts || !offsets || !out))) { ycr_set_error("bad resample arguments"); return YCR_E_ARG; }
+    return launch_resample(pts, offsets, S, n_out, out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t ycr_bbox_loss_workspace_bytes(int B, int A) { return (B > 0 && A > 0) ? bbox_loss_workspace_bytes(B, A) : 0; }

@@ -64,3 +64,25 @@ def non_max_suppression(
     n = counts.tolist()
     del cls_t
     return [rows[i, :n[i]] for i in range(B)]
+
+
+def resample_segments(segments, n=1000, device=None):
+    """utils/ops.py:676-693 — list of (m_i, 2) polygons (numpy arrays or tensors) -> list of (n, 2) float32
+    tensors on the device, each polygon closed and linearly resampled to n points; values are bit-identical
+    to the reference's numpy implementation.  One kernel launch for the whole list."""
+    import numpy as np
+    if len(segments) == 0:
+        return []
+    ts = [torch.as_tensor(np.asarray(s) if not torch.is_tensor(s) else s, dtype=torch.float32).reshape(-1, 2)
+          for s in segments]
+    dev = torch.device(device) if device is not None else next((t.device for t in ts if t.is_cuda), torch.device("cuda"))
+    if dev.type != "cuda":
+        raise L.YcrError("ycr_b200 kernels need a CUDA device; there is no CPU path")
+    offs = torch.zeros(len(ts) + 1, dtype=torch.int32)
+    offs[1:] = torch.cumsum(torch.tensor([t.shape[0] for t in ts]), 0)
+    pts = torch.cat([t.to(dev) for t in ts]).contiguous()
+    offs_d = offs.to(dev)
+    out = torch.empty(len(ts), int(n), 2, device=dev, dtype=torch.float32)
+    rc = L.lib().ycr_resample_segments(pts.data_ptr(), offs_d.data_ptr(), len(ts), int(n), out.data_ptr(), L.stream_ptr(dev))
+    L.check(rc, "ycr_resample_segments")
+    return list(out.unbind(0))
