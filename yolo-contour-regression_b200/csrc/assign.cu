@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
             cur_bg = bg;
         }
-        if (tid == 0) { sm.qcount = 0; sm.q2count = 0; }
         __syncthreads();
         const int c = (work - ws.chunk_off[bg]) * NT + tid;
         const bool active = c < ws.ncand[bg];
@@ -206,14 +205,12 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
             polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
         }
-        polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
-        __syncthreads();
-        polar_settle_queue<R, NT>(sm, a.pc, tid);
-        __syncthreads();
-        if (tid == 0) {
-            atomicAdd(&g_ycr_stats[0], (unsigned long long)min(NT, ws.ncand[bg] - (work - ws.chunk_off[bg]) * NT));
-            atomicAdd(&g_ycr_stats[1], (unsigned long long)sm.qcount);
-            atomicAdd(&g_ycr_stats[2], (unsigned long long)sm.q2count);
+        const int nq = polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        const int nscan = polar_settle_queue<R, NT>(sm, a.pc, tid, nq);
+        if ((tid & 31) == 0) {
+            atomicAdd(&g_ycr_stats[0], (unsigned long long)max(0, min(32, ws.ncand[bg] - (work - ws.chunk_off[bg]) * NT - (tid & ~31))));
+            atomicAdd(&g_ycr_stats[1], (unsigned long long)nq);
+            atomicAdd(&g_ycr_stats[2], (unsigned long long)nscan);
         }
         if (active) {
             const int b = bg / a.gt.G;
@@ -461,7 +458,6 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
     const int base = pa.img_base[b];
     for (int r0 = 0; r0 < cnt; r0 += NT) {
         __syncthreads();
-        if (tid == 0) { sm.qcount = 0; sm.q2count = 0; }
         __syncthreads();
         const int r = r0 + tid;
         const bool active = r < cnt;
@@ -474,10 +470,8 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
             polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
         }
-        polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
-        __syncthreads();
-        polar_settle_queue<R, NT>(sm, a.pc, tid);
-        __syncthreads();
+        const int nq = polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        polar_settle_queue<R, NT>(sm, a.pc, tid, nq);
         if (!active) continue;
         const int grow = base + row;
         float tmin = 3.4e38f, tmax = 0.f;

@@ -52,9 +52,7 @@ struct PolarSmem {
     float2 anchor[NT];
     unsigned char cnt[R][NT];          // points per bin (saturating at 255)
     float tval[R][NT];                 // settled ray targets
-    unsigned short queue[NT * R / 2];  // (thread << 7) | ray : pairs the own bin could not settle;
-                                       // bit 15 is set later on pairs that need the exact scan
-    int qcount, q2count;
+    unsigned short queue[NT / 32][16 * R];  // per warp: (thread << 7) | ray of the pairs the own bin could not settle
 };
 
 // sorted insert with depth-2 dependency: new k_i = max(k_{i-1}, min(k_i, x))
@@ -207,12 +205,16 @@ __device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, cons
     return fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
 }
 
-// Own-bin settlement of every ray of this thread; unsettled rays go to the block queue.
-// On return sm.tval[i][tid] holds the target of every settled ray (the lists stay intact).
+// Own-bin settlement of every ray of this thread; unsettled rays go to the queue of the thread's warp
+// (warps never touch each other's candidates, so the whole settlement needs no block barrier).
+// Returns the warp-uniform number of queued pairs.  On return sm.tval[i][tid] holds the target of every
+// settled ray (the lists stay intact).
 template <int R, int NT>
-__device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, bool active,
-                                                 float ax, float ay) {
+__device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, bool active,
+                                                float ax, float ay) {
     const unsigned lane = threadIdx.x & 31u;
+    unsigned short* wq = sm.queue[tid >> 5];
+    int nq = 0;
     for (int i = 0; i < R; ++i) {
         bool unsettled = false;
         if (active) {
@@ -233,21 +235,20 @@ __device__ __forceinline__ void polar_settle_own(PolarSmem<R, NT>& sm, const Pol
         }
         const unsigned ball = __ballot_sync(0xffffffffu, unsettled);
         if (ball) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&sm.qcount, __popc(ball));
-            base = __shfl_sync(0xffffffffu, base, 0);
             if (unsettled) {
-                const int slot = base + __popc(ball & ((1u << lane) - 1u));
-                if (slot < NT * R / 2) {
-                    sm.queue[slot] = (unsigned short)((tid << 7) | i);
-                } else {  // queue full (pathological block): settle right here, serially
+                const int slot = nq + __popc(ball & ((1u << lane) - 1u));
+                if (slot < 16 * R) {
+                    wq[slot] = (unsigned short)((tid << 7) | i);
+                } else {  // queue full (pathological warp): settle right here, serially
                     float t;
                     if (!polar_settle_pair<R, NT>(sm, pc, tid, i, t)) t = polar_scan_serial<R, NT>(sm, pc, tid, i);
                     sm.tval[i][tid] = t;
                 }
             }
+            nq += __popc(ball);
         }
     }
+    return min(nq, 16 * R);
 }
 
 // Smallest window (in bins on each side of the ray) whose bins hold at least four points and that
@@ -387,30 +388,37 @@ __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, con
 }
 
 
-// Block-wide: settle all queued pairs (any thread may serve any owner), then the exact-scan queue.
-// Must be called by all NT threads; contains block barriers.
+// Warp-wide: settle the warp's queued pairs, 32 at a time; a pair whose neighbourhood settlement cannot
+// be certified is scanned exactly by the whole warp right away.  No block barrier.  Returns the number of
+// exact scans (statistics).
 template <int R, int NT>
-__device__ __forceinline__ void polar_settle_queue(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid) {
-    const int nq = min(sm.qcount, NT * R / 2);
-    int nfail = 0;
-    for (int q = tid; q < nq; q += NT) {
-        const unsigned e = sm.queue[q];
-        const int owner = e >> 7, ray = e & 127u;
-        float t;
-        if (polar_settle_pair<R, NT>(sm, pc, owner, ray, t)) sm.tval[ray][owner] = t;
-        else { sm.queue[q] = (unsigned short)(e | 0x8000u); ++nfail; }
-    }
-    if (nfail) atomicAdd(&sm.q2count, nfail);
-    __syncthreads();
-    if (sm.q2count == 0) return;
+__device__ __forceinline__ int polar_settle_queue(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, int nq) {
     const unsigned lane = tid & 31u;
-    for (int q = tid >> 5; q < nq; q += NT / 32) {
-        const unsigned e = sm.queue[q];
-        if (!(e & 0x8000u)) continue;  // warp-uniform: every lane reads the same entry
-        const int owner = (e & 0x7FFFu) >> 7, ray = e & 127u;
-        const float t = polar_scan_pair<R, NT>(sm, pc, owner, ray, lane);
-        if (lane == 0) sm.tval[ray][owner] = t;
+    const unsigned short* wq = sm.queue[tid >> 5];
+    int nscan = 0;
+    __syncwarp();
+    for (int q0 = 0; q0 < nq; q0 += 32) {
+        const int q = q0 + (int)lane;
+        unsigned e = 0;
+        bool failed = false;
+        if (q < nq) {
+            e = wq[q];
+            float t;
+            if (polar_settle_pair<R, NT>(sm, pc, (int)(e >> 7), (int)(e & 127u), t)) sm.tval[e & 127u][e >> 7] = t;
+            else failed = true;
+        }
+        unsigned fm = __ballot_sync(0xffffffffu, failed);
+        nscan += __popc(fm);
+        while (fm) {
+            const int src = __ffs(fm) - 1;
+            fm &= fm - 1;
+            const unsigned es = __shfl_sync(0xffffffffu, e, src);
+            const float t = polar_scan_pair<R, NT>(sm, pc, (int)(es >> 7), (int)(es & 127u), lane);
+            if (lane == 0) sm.tval[es & 127u][es >> 7] = t;
+        }
     }
+    __syncwarp();
+    return nscan;
 }
 
 static inline double ycr_deg2rad(double d) { return d * 3.14159265358979323846 / 180.0; }
