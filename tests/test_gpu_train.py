@@ -311,3 +311,38 @@ def test_capacity_overflow_is_loud():
     assert torch.isfinite(total)
     total, items = crit.call_packed(feats, packed, 8)
     assert torch.isnan(total) and bool(torch.isnan(items).all())
+
+
+def test_positive_targets_gather_equals_resweep():
+    """The positives' ray targets come either from the rows K1 stored (default) or from a second sweep
+    (when the store would not fit the budget): both paths must agree bit for bit."""
+    import os
+    from ycr_b200.loss import v8SegmentationLoss
+    from ycr_b200.tal import TaskAlignedAssigner
+    from ycr_b200 import synth
+    dev = _dev()
+    g = load_golden("train_s320_ragged")
+    cfg, feats, batch = train_inputs(g)
+    cpu, gpu, shapes = _assigner_inputs(cfg, feats, batch, dev)
+    res = {}
+    for mode, env in (("gather", None), ("resweep", "0")):
+        if env is None:
+            os.environ.pop("YCR_T_STORE_MAX_BYTES", None)
+        else:
+            os.environ["YCR_T_STORE_MAX_BYTES"] = env
+        try:
+            asg = TaskAlignedAssigner(topk=10, num_classes=cfg.nc, alpha=0.5, beta=4.0)
+            out = asg(gpu["scores"], gpu["rays"], gpu["anc"], gpu["gl"], gpu["gb"], gpu["mask_gt"], gpu["gc"],
+                      gpu["st"], gpu["ss"], 0, None, grid=(shapes, list(cfg.strides)))
+            crit = v8SegmentationLoss(nc=cfg.nc, nm=cfg.rays, strides=cfg.strides, device=dev)
+            fg = [f.to(dev).requires_grad_(True) for f in feats]
+            total, items = crit((fg, 5, 2), batch)
+            total.backward()
+            res[mode] = (out[5].clone(), out[6].clone(), total.detach().clone(), [f.grad.clone() for f in fg])
+        finally:
+            os.environ.pop("YCR_T_STORE_MAX_BYTES", None)
+    a, b = res["gather"], res["resweep"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    for x, y in zip(a[3], b[3]):
+        assert torch.equal(x, y)
+    assert rel_err(a[0].cpu(), g["asg_gt_dist"]) < TOL

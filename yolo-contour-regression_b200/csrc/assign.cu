@@ -6,6 +6,7 @@
 // Reference: utils/tal.py:1135-1390, :52-66, :214-248, :1445-1464 (file:line under
 // /root/reference/ultralytics-main/ultralytics/).  No (B,G,A) float tensor is materialised.
 #include "train_path.cuh"
+#include <stdlib.h>
 
 #define K1_NT 64
 #define K3_NT 512
@@ -231,6 +232,11 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             float score = a.pred.cls[l][(int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
                                         (int64_t)label * a.pred.cls_sc[l]];
             if (a.pred.cls_is_logit) score = 1.f / (1.f + expf(-score));
+            if (ws.cand_t) {
+                float* tp = ws.cand_t + (int64_t)work * R * NT + tid;
+#pragma unroll 4
+                for (int i = 0; i < R; ++i) tp[i * NT] = sm.tval[i][tid];
+            }
             const int64_t m = (int64_t)ws.cand_off[bg] + c;
             ws.cand_ov[m] = ov;
             ws.cand_align[m] = align_of(score, ov, a.cfg.alpha, a.cfg.beta);
@@ -511,6 +517,60 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
     }
 }
 
+// K4 (gather form): when K1 kept the ray targets of every candidate, a positive's targets are just read
+// back - one thread per positive; same outputs as k_positive_targets.
+template <int R>
+__global__ void __launch_bounds__(128) k_positive_gather(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                                         const PosArgs pa) {
+    const int b = blockIdx.y;
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    if (row >= ws.npos[b]) return;
+    const int an = ws.pos_anchor[(int64_t)b * ws.pos_cap + row];
+    const int g = ws.pos_g[(int64_t)b * ws.pos_cap + row];
+    const int bg = b * a.gt.G + g;
+    const AnchorPos ap = anchor_pos(a.grid, an);
+    const int ci = ws.valid[bg] ? cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, ap) : -1;
+    const float* tp = nullptr;
+    if (ci >= 0) tp = ws.cand_t + ((int64_t)(ws.chunk_off[bg] + ci / K1_NT) * R) * K1_NT + (ci % K1_NT);
+    const int grow = pa.img_base[b] + row;
+    float t[R];
+    float tmin = 3.4e38f, tmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        t[i] = tp ? tp[i * K1_NT] : YCR_FLOOR;
+        tmin = fminf(tmin, t[i]);
+        tmax = fmaxf(tmax, t[i]);
+        if (pa.gt_dist && grow < pa.pos_capacity) pa.gt_dist[(int64_t)grow * R + i] = t[i];
+    }
+    if (pa.centerness && grow < pa.pos_capacity) pa.centerness[grow] = sqrtf(tmin / tmax);
+    if (pa.with_loss) {
+        const int l = ap.level;
+        const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+        const int64_t sc = a.pred.rays_sc[l];
+        const float rs = a.pred.ray_scale[l];
+        float p[R];
+        float smin = 0.f, smax = 0.f;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            p[i] = rp[i * sc] * rs;
+            smin += fmaxf(fminf(p[i], t[i]), YCR_FLOOR);
+            smax += fmaxf(p[i], t[i]);
+        }
+        const float w = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
+        ws.pos_loss[(int64_t)b * ws.pos_cap + row] = logf(smax / smin) * w;
+        const float coef = w / pa.tss[0] * pa.box_gain * (float)a.gt.B * rs;
+        const float imax = 1.f / smax, imin = 1.f / smin;
+        float* gp = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            float gr = 0.f;
+            if (p[i] >= t[i]) gr += imax;                       // max() routes to pred (first index on ties)
+            if (p[i] <= t[i] && p[i] >= YCR_FLOOR) gr -= imin;  // min() routes to pred; clamp passes when >= floor
+            gp[i] = gr * coef;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dense API outputs of TaskAlignedAssigner.forward (get_targets utils/tal.py:1340-1390)
 // ------------------------------------------------------------------------------------------------
@@ -576,6 +636,15 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
     w.err = al.take<int>(1);
     w.cand_align = al.take<float>((size_t)cand_cap + 1);
     w.cand_ov = al.take<float>((size_t)cand_cap + 1);
+    {
+        // keep the ray targets of every candidate when that is affordable (C2: 72 MB); the positives are then
+        // a gather instead of a second sweep.  YCR_T_STORE_MAX_BYTES overrides the 1 GiB budget (0 = never).
+        const char* env = getenv("YCR_T_STORE_MAX_BYTES");
+        const size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : ((size_t)1 << 30);
+        const size_t chunks_cap = (size_t)cand_cap / K1_NT + (size_t)BG + 1;
+        const size_t bytes = chunks_cap * R * K1_NT * sizeof(float);
+        w.cand_t = (bytes <= budget && BG > 0) ? al.take<float>(chunks_cap * R * K1_NT) : nullptr;
+    }
     w.sel = al.take<int>((size_t)BG * topk + 1);
     w.npos = al.take<int>(B + 1);
     w.pos_anchor = al.take<int>((size_t)B * pos_cap);
@@ -644,6 +713,13 @@ int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_d
     PosArgs pa{gt_dist, centerness, pos_capacity, img_base, tss, with_loss ? 1 : 0, lcfg ? lcfg->box_gain : 0.f};
     if (BG == 0) return YCR_OK;
     YcrProfScope ps(YCR_T_POS, st);
+    if (ws.cand_t) {
+        dim3 grid((ws.pos_cap + 127) / 128, B);
+        if (a.cfg.rays == 36) k_positive_gather<36><<<grid, 128, 0, st>>>(a, ws, pa);
+        else k_positive_gather<72><<<grid, 128, 0, st>>>(a, ws, pa);
+        YCR_LAUNCH_CHECK();
+        return YCR_OK;
+    }
     if (a.cfg.rays == 36) {
         const size_t smem = sizeof(PolarSmem<36, K4_NT>);
         YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -16,6 +16,7 @@ struct AssignWs {
     // K1: per-candidate metrics
     float* cand_align; // [cap]
     float* cand_ov;    // [cap]
+    float* cand_t;     // [chunks][R][K1 block] ray targets of every candidate, or null (then positives are re-swept)
     // K2: per-GT top-k
     int* sel;          // [BG][topk] anchor index or -1
     // K3: per-image positives, padded to pos_cap = G*topk rows per image
