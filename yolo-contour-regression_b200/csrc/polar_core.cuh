@@ -42,6 +42,7 @@ struct PolarConst {
     float pk_gate;            // pseudo-angle of 3 deg
     float tan_win[YCR_MAXWIN];  // tan((2m+1)*hw + 5 TOL), 0 when that is 89 deg or more
     int m_gate;               // smallest window with (2m+1)*hw - 3 TOL > 3 deg
+    uint32_t q2_gate;         // pseudo-angle of 3 deg in the 2^-21 fixed point of pack_pseudo
 };
 
 template <int R, int NT>
@@ -64,22 +65,37 @@ __device__ __forceinline__ void insert4(uint32_t& k0, uint32_t& k1, uint32_t& k2
     k1 = n1; k2 = n2; k3 = n3;
 }
 
-// Monotone map of the angle between v and the ray onto [0,4], from q=|cross| and d=dot.
+// Monotone map of the angle between v and the ray onto [0,4), from q=|cross| and d=dot: tan in the first
+// octant pair, 2 - cot up to 135 deg, 4 + tan beyond.  Branch-free: one select chain, one fast division
+// (2 ulp on a key whose decisive gaps are margin-checked at >= 1e-4 deg).
 __device__ __forceinline__ float pseudo_angle(float q, float d) {
-    // (approximate division: 2 ulp on a key whose decisive gaps are margin-checked at >= 1e-4 deg)
-    if (d >= q) return (d > 0.f) ? __fdividef(q, d) : 0.f;
-    if (d > -q) return 2.f - __fdividef(d, q);
-    return 4.f + __fdividef(q, d);
+    const bool near = d >= q, mid = d > -q;
+    const float num = near ? q : (mid ? -d : q);
+    const float den = near ? d : (mid ? q : d);
+    const float off = near ? 0.f : (mid ? 2.f : 4.f);
+    const float k = off + ((den != 0.f) ? __fdividef(num, den) : 0.f);
+    return fminf(k, 3.9999995f);
 }
 
-// float sorted insert of (k, v) into four slots
-__device__ __forceinline__ void finsert4(float (&fk)[4], float (&fv)[4], float k, float v) {
-    if (k < fk[3]) {
+// pseudo-angle and point index as one sortable word: 23-bit fixed point (2^-21 units, ~3e-5 deg) | 9-bit index
+__device__ __forceinline__ uint32_t pack_pseudo(float k, int j) {
+    return (__float_as_uint(fmaf(k, 2097152.f, 8388608.f)) << 9) | (uint32_t)j;
+}
+
+// largest squared distance among the (up to four) contour points packed in K, seen from a
+template <int R, int NT>
+__device__ __forceinline__ float max_dist2(const PolarSmem<R, NT>& sm, const uint4 K, const float2 a) {
+    const uint32_t e[4] = {K.x, K.y, K.z, K.w};
+    float m = 0.f;
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
-            if (k < fk[s]) { float t = fk[s]; fk[s] = k; k = t; t = fv[s]; fv[s] = v; v = t; }
-        if (k < fk[3]) { fk[3] = k; fv[3] = v; }
+    for (int s = 0; s < 4; ++s) {
+        if (e[s] != YCR_EMPTY) {
+            const float2 p = sm.contour[e[s] & 511u];
+            const float vx = p.x - a.x, vy = p.y - a.y;
+            m = fmaxf(m, fmaf(vx, vx, vy * vy));
+        }
     }
+    return m;
 }
 
 // One sweep over the contour for the anchor (ax, ay) of this thread.  The per-ray lists stay in
@@ -187,22 +203,21 @@ template <int R, int NT>
 __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
                                                   float& result);
 
-// Exact scan of all points by one thread (only used when the block queue overflows).
+// Exact scan of all points by one thread (only used when a warp queue overflows).
 template <int R, int NT>
 __device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray) {
     const float2 a = sm.anchor[owner];
     const float2 cs = sm.raydir[ray];
-    float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 K = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
     for (int j = 0; j < YCR_C; ++j) {
         const float2 p = sm.contour[j];
         float vx = p.x - a.x;
         const float vy = p.y - a.y;
-        const float l2 = fmaf(vx, vx, vy * vy);
-        if (l2 == 0.f) vx = 1.f;
-        finsert4(fk, fd, pseudo_angle(fabsf(fmaf(vy, cs.x, -vx * cs.y)), fmaf(vx, cs.x, vy * cs.y)), l2);
+        if (vx == 0.f && vy == 0.f) vx = 1.f;
+        insert4(K.x, K.y, K.z, K.w, pack_pseudo(pseudo_angle(fabsf(fmaf(vy, cs.x, -vx * cs.y)), fmaf(vx, cs.x, vy * cs.y)), j));
     }
-    if (fk[0] > pc.pk_gate) return YCR_FLOOR;
-    return fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
+    if ((K.x >> 9) > pc.q2_gate) return YCR_FLOOR;
+    return fmaxf(sqrtf(max_dist2<R, NT>(sm, K, a)), YCR_FLOOR);
 }
 
 // Own-bin settlement of every ray of this thread; unsettled rays go to the queue of the thread's warp
@@ -312,20 +327,19 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
         }
     }
     if (dmax - dmin > 16) return false;
-    float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 K = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
     int n_in = 0, n_maybe = 0;
-    auto eval = [&](int d) -> float {  // contour point j0 + d (mod C)
+    auto eval = [&](int d) -> float {  // contour point j0 + d (mod C); branch-free
         int j = j0 + d;
         j = (j < 0) ? j + YCR_C : ((j >= YCR_C) ? j - YCR_C : j);
         const float2 p = sm.contour[j];
         float vx = p.x - a.x;
         const float vy = p.y - a.y;
-        const float l2 = fmaf(vx, vx, vy * vy);
-        if (l2 == 0.f) vx = 1.f;
+        if (vx == 0.f && vy == 0.f) vx = 1.f;
         const float k = pseudo_angle(fabsf(fmaf(vy, cs.x, -vx * cs.y)), fmaf(vx, cs.x, vy * cs.y));
         n_in += (k < win_lo) ? 1 : 0;
         n_maybe += (k < win_hi) ? 1 : 0;
-        finsert4(fk, fd, k, l2);
+        insert4(K.x, K.y, K.z, K.w, pack_pseudo(k, j));
         return k;
     };
     int lo = dmin - YCR_NBR, hi = dmax + YCR_NBR;
@@ -340,14 +354,15 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
     int h = 0;
     while (khi < win_hi && h < YCR_GROW) { khi = eval(++hi); ++h; }
     if (g >= YCR_GROW || h >= YCR_GROW || n_in != n_maybe || n_in != nbins) return false;
-    result = (fk[0] > pc.pk_gate) ? YCR_FLOOR : fmaxf(sqrtf(fmaxf(fmaxf(fd[0], fd[1]), fmaxf(fd[2], fd[3]))), YCR_FLOOR);
+    result = ((K.x >> 9) > pc.q2_gate) ? YCR_FLOOR : fmaxf(sqrtf(max_dist2<R, NT>(sm, K, a)), YCR_FLOOR);
     return true;
 }
 
 // Exact scan of all points for one pair, one warp per pair (lanes take consecutive points).  When the
 // bin counts bound the window that holds the four nearest points, points outside it are skipped after
 // a two-instruction test, so only the one or two iterations whose 32 consecutive points touch the
-// window pay for key evaluation and insertion.
+// window pay for key evaluation and insertion.  The four smallest of the lanes' packed keys are then
+// popped with one warp min-reduction each (keys are unique: they carry the point index).
 template <int R, int NT>
 __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, const PolarConst& pc, int owner, int ray,
                                                  unsigned lane) {
@@ -356,35 +371,26 @@ __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, con
     int m, nbins;
     float tanw = 0.f;
     if (polar_window<R, NT>(sm, pc, owner, ray, m, nbins)) tanw = pc.tan_win[m];  // 0: no usable bound
-    float fk[4] = {1e30f, 1e30f, 1e30f, 1e30f}, fd[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 K = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
     for (int j = lane; j < YCR_C; j += 32) {
         const float2 p = sm.contour[j];
         float vx = p.x - a.x;
         const float vy = p.y - a.y;
-        const float l2 = fmaf(vx, vx, vy * vy);
-        if (l2 == 0.f) vx = 1.f;
+        if (vx == 0.f && vy == 0.f) vx = 1.f;
         const float d = fmaf(vx, cs.x, vy * cs.y);
         const float q = fabsf(fmaf(vy, cs.x, -vx * cs.y));
-        if (tanw == 0.f || q <= tanw * d) finsert4(fk, fd, pseudo_angle(q, d), l2);
+        if (tanw == 0.f || q <= tanw * d) insert4(K.x, K.y, K.z, K.w, pack_pseudo(pseudo_angle(q, d), j));
     }
-    float first = 0.f, maxd = 0.f;
+    uint4 W;
+    uint32_t* w = &W.x;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        float mn = fk[0];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        const unsigned who = __ballot_sync(0xffffffffu, fk[0] == mn);
-        const int src = __ffs(who) - 1;
-        const float dsel = __shfl_sync(0xffffffffu, fd[0], src);
-        if ((int)lane == src) {
-            fk[0] = fk[1]; fk[1] = fk[2]; fk[2] = fk[3]; fk[3] = 1e30f;
-            fd[0] = fd[1]; fd[1] = fd[2]; fd[2] = fd[3];
-        }
-        if (r == 0) first = mn;
-        maxd = fmaxf(maxd, dsel);
+        const uint32_t mn = __reduce_min_sync(0xffffffffu, K.x);
+        if (K.x == mn && mn != YCR_EMPTY) { K.x = K.y; K.y = K.z; K.z = K.w; K.w = YCR_EMPTY; }
+        w[r] = mn;
     }
-    if (first > pc.pk_gate) return YCR_FLOOR;
-    return fmaxf(sqrtf(maxd), YCR_FLOOR);
+    if ((W.x >> 9) > pc.q2_gate) return YCR_FLOOR;
+    return fmaxf(sqrtf(max_dist2<R, NT>(sm, W, a)), YCR_FLOOR);
 }
 
 
@@ -455,6 +461,7 @@ static inline PolarConst make_polar_const(int R) {
     pc.pk_lo[R / 2] = 5.f;
     pc.pk_hi[R / 2] = 5.f;
     pc.pk_gate = (float)ycr_pseudo_host(YCR_GATE_DEG);
+    pc.q2_gate = (uint32_t)(ycr_pseudo_host(YCR_GATE_DEG) * 2097152.0);
     pc.m_gate = 0;
     while ((2 * pc.m_gate + 1) * hw - 3 * T <= YCR_GATE_DEG) ++pc.m_gate;
     for (int m = 0; m < YCR_MAXWIN; ++m) {
