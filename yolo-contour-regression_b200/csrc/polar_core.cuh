@@ -25,6 +25,9 @@
 // tests (~1e-5 deg).  It only decides WHICH exact path settles a ray, never the result; a point inside the
 // +-3 TOL zone around a window edge sends the ray to the exact scan.
 #define YCR_TOL_DEG 0.001
+#ifndef YCR_GROUP
+#define YCR_GROUP 4   // contour points fetched / inserted / stored together in the sweep
+#endif
 #define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
 #define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
 
@@ -111,11 +114,11 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
     int ray = 0;
     float cr = 1.f, sr = 0.f;
     const float tan_in = pc.tan_in, ks = pc.key_scale;
-    for (int j0 = 0; j0 < YCR_C; j0 += 4) {
+    for (int j0 = 0; j0 < YCR_C; j0 += YCR_GROUP) {
         // phase 1: everything that does not depend on the current bin, four points at once
-        float vx[4], vy[4], inv[4];
+        float vx[YCR_GROUP], vy[YCR_GROUP], inv[YCR_GROUP];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < YCR_GROUP; ++u) {
             const float2 p = sm.contour[j0 + u];
             vx[u] = p.x - ax;
             vy[u] = p.y - ay;
@@ -127,14 +130,14 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
         // The usual move - one bin up or down - is branch-free: cross/dot and the ray direction are
         // rotated by one ray spacing in registers; the exact direction is reloaded from the table at
         // the start of every group, so at most four rotations (a few 1e-6 deg) ever accumulate.
-        int rb[4];
-        uint32_t pk[4];
+        int rb[YCR_GROUP];
+        uint32_t pk[YCR_GROUP];
         {
             const float2 cs = sm.raydir[ray];
             cr = cs.x; sr = cs.y;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < YCR_GROUP; ++u) {
             float dot = fmaf(vx[u], cr, vy[u] * sr);
             float crs = fmaf(vy[u], cr, -vx[u] * sr);
             const bool need = !(fabsf(crs) <= tan_in * dot);
@@ -164,17 +167,17 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             pk[u] = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
         }
         // phase 3: the four lists and counts are fetched together ...
-        uint4 L[4];
-        unsigned c[4];
+        uint4 L[YCR_GROUP];
+        unsigned c[YCR_GROUP];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < YCR_GROUP; ++u) {
             L[u] = sm.list[rb[u]][tid];
             c[u] = sm.cnt[rb[u]][tid];
         }
         // phase 4: ... updated in contour order, forwarding the result of an earlier point of the same
         // bin (the usual case) instead of going through shared memory again ...
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < YCR_GROUP; ++u) {
 #pragma unroll
             for (int w = 0; w < u; ++w)
                 if (rb[w] == rb[u]) { L[u] = L[w]; c[u] = c[w]; }
@@ -183,7 +186,7 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
         }
         // phase 5: ... and written back in order (a later store to the same bin carries all updates)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < YCR_GROUP; ++u) {
             sm.list[rb[u]][tid] = L[u];
             sm.cnt[rb[u]][tid] = (unsigned char)c[u];
         }
