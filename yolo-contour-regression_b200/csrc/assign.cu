@@ -138,8 +138,11 @@ __global__ void __launch_bounds__(1024) k_gt_setup(GridDev grid, ycr_gt_t gt, As
         ws.cand_off[bg] = run_c;
         ws.chunk_off[bg] = run_k;
         const int n = ws.ncand[bg];
+        const int nk = (n + chunk - 1) / chunk;
+        for (int k = 0; k < nk; ++k)
+            if (run_k + k < ws.chunks_cap) ws.chunk_bg[run_k + k] = bg;
         run_c += n;
-        run_k += (n + chunk - 1) / chunk;
+        run_k += nk;
     }
     if (t == 1023) {
         ws.cand_off[BG] = s_c[1023];
@@ -175,18 +178,12 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
     const int tid = threadIdx.x;
-    const int BG = a.gt.B * a.gt.G;
     const int T = ws.totals[1];
     if (ws.err[0]) return;
     init_raydir<R, NT>(sm, tid);
     int cur_bg = -1;
     for (int work = blockIdx.x; work < T; work += gridDim.x) {
-        int lo = 0, hi = BG;
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (ws.chunk_off[mid] <= work) lo = mid; else hi = mid;
-        }
-        const int bg = lo;
+        const int bg = ws.chunk_bg[work];
         __syncthreads();
         if (bg != cur_bg) {
             const float* cp = a.gt.coor + (int64_t)bg * a.gt.coor_stride;
@@ -631,6 +628,9 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
     w.ncand = al.take<int>(BG + 1);
     w.cand_off = al.take<int>(BG + 1);
     w.chunk_off = al.take<int>(BG + 1);
+    const size_t chunks_cap = (size_t)cand_cap / K1_NT + (size_t)BG + 1;  // every GT adds at most one partial chunk
+    w.chunk_bg = al.take<int>(chunks_cap);
+    w.chunks_cap = (int)chunks_cap;
     w.valid = al.take<uint8_t>(BG + 1);
     w.totals = al.take<int>(2);
     w.err = al.take<int>(1);
@@ -641,7 +641,6 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
         // a gather instead of a second sweep.  YCR_T_STORE_MAX_BYTES overrides the 1 GiB budget (0 = never).
         const char* env = getenv("YCR_T_STORE_MAX_BYTES");
         const size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : ((size_t)1 << 30);
-        const size_t chunks_cap = (size_t)cand_cap / K1_NT + (size_t)BG + 1;
         const size_t bytes = chunks_cap * R * K1_NT * sizeof(float);
         w.cand_t = (bytes <= budget && BG > 0) ? al.take<float>(chunks_cap * R * K1_NT) : nullptr;
     }

@@ -10,6 +10,8 @@ struct AssignWs {
     int* ncand;        // [BG]
     int* cand_off;     // [BG+1]
     int* chunk_off;    // [BG+1]
+    int* chunk_bg;     // [chunks_cap] GT of every chunk (saves the per-chunk binary search in K1)
+    int chunks_cap;
     uint8_t* valid;    // [BG]
     int* totals;       // [2] = {M, T}
     int* err;          // [1] device error flag (candidate capacity exceeded)
