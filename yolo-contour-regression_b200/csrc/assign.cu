@@ -8,7 +8,9 @@
 #include "train_path.cuh"
 #include <stdlib.h>
 
+#ifndef K1_NT
 #define K1_NT 64
+#endif
 #define K3_NT 512
 #define K4_NT 32   // positives per GT are ~topk: one warp per block
 
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
 #pragma unroll 4
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
-                const float t = sm.tval[i][tid];
+                const float t = sm.tv(i, tid);
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             if (ws.cand_t) {
                 float* tp = ws.cand_t + (int64_t)work * R * NT + tid;
 #pragma unroll 4
-                for (int i = 0; i < R; ++i) tp[i * NT] = sm.tval[i][tid];
+                for (int i = 0; i < R; ++i) tp[i * NT] = sm.tv(i, tid);
             }
             const int64_t m = (int64_t)ws.cand_off[bg] + c;
             ws.cand_ov[m] = ov;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
         const int grow = base + row;
         float tmin = 3.4e38f, tmax = 0.f;
         for (int i = 0; i < R; ++i) {
-            const float t = sm.tval[i][tid];
+            const float t = sm.tv(i, tid);
             tmin = fminf(tmin, t);
             tmax = fmaxf(tmax, t);
             if (pa.gt_dist && grow < pa.pos_capacity) pa.gt_dist[(int64_t)grow * R + i] = t;
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             float smin = 0.f, smax = 0.f;
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
-                const float t = sm.tval[i][tid];
+                const float t = sm.tv(i, tid);
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             float* gp = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
-                const float t = sm.tval[i][tid];
+                const float t = sm.tv(i, tid);
                 float g = 0.f;
                 if (p >= t) g += imax;                       // max() routes to pred (first index on ties)
                 if (p <= t && p >= YCR_FLOOR) g -= imin;     // min() routes to pred; clamp passes when >= floor

@@ -55,8 +55,11 @@ struct PolarSmem {
     float2 raydir[R];                  // (cos, sin) of i*360/R deg
     float2 anchor[NT];
     unsigned char cnt[R][NT];          // points per bin (saturating at 255)
-    float tval[R][NT];                 // settled ray targets
     unsigned short queue[NT / 32][16 * R];  // per warp: (thread << 7) | ray of the pairs the own bin could not settle
+    // Settled ray target of (ray i, thread t).  It takes the place of the fourth key of that list: once a
+    // ray is settled nothing reads its list again except the .x a neighbouring ray may borrow.
+    __device__ __forceinline__ float& tv(int i, int t) { return reinterpret_cast<float*>(&list[i][t])[3]; }
+    __device__ __forceinline__ float tv(int i, int t) const { return reinterpret_cast<const float*>(&list[i][t])[3]; }
 };
 
 // sorted insert with depth-2 dependency: new k_i = max(k_{i-1}, min(k_i, x))
@@ -225,7 +228,7 @@ __device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, cons
 
 // Own-bin settlement of every ray of this thread; unsettled rays go to the queue of the thread's warp
 // (warps never touch each other's candidates, so the whole settlement needs no block barrier).
-// Returns the warp-uniform number of queued pairs.  On return sm.tval[i][tid] holds the target of every
+// Returns the warp-uniform number of queued pairs.  On return sm.tv(i, tid) holds the target of every
 // settled ray (the lists stay intact).
 template <int R, int NT>
 __device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, bool active,
@@ -239,14 +242,14 @@ __device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const Pola
             const uint4 L = sm.list[i][tid];
             const bool own_gate = (L.x == YCR_EMPTY) || ((L.x >> 9) > pc.q_gate);
             if (own_gate && pc.gate_l1) {
-                sm.tval[i][tid] = YCR_FLOOR;
+                sm.tv(i, tid) = YCR_FLOOR;
             } else if (L.w != YCR_EMPTY && (L.w >> 9) < pc.q_res) {
                 // (for hw < 3 deg every in-bin key is below the gate, so the gate cannot fire here)
                 float m = dist2_of(sm, L.x, ax, ay);
                 m = fmaxf(m, dist2_of(sm, L.y, ax, ay));
                 m = fmaxf(m, dist2_of(sm, L.z, ax, ay));
                 m = fmaxf(m, dist2_of(sm, L.w, ax, ay));
-                sm.tval[i][tid] = fmaxf(sqrtf(m), YCR_FLOOR);
+                sm.tv(i, tid) = fmaxf(sqrtf(m), YCR_FLOOR);
             } else {
                 unsettled = true;
             }
@@ -260,7 +263,7 @@ __device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const Pola
                 } else {  // queue full (pathological warp): settle right here, serially
                     float t;
                     if (!polar_settle_pair<R, NT>(sm, pc, tid, i, t)) t = polar_scan_serial<R, NT>(sm, pc, tid, i);
-                    sm.tval[i][tid] = t;
+                    sm.tv(i, tid) = t;
                 }
             }
             nq += __popc(ball);
@@ -413,7 +416,7 @@ __device__ __forceinline__ int polar_settle_queue(PolarSmem<R, NT>& sm, const Po
         if (q < nq) {
             e = wq[q];
             float t;
-            if (polar_settle_pair<R, NT>(sm, pc, (int)(e >> 7), (int)(e & 127u), t)) sm.tval[e & 127u][e >> 7] = t;
+            if (polar_settle_pair<R, NT>(sm, pc, (int)(e >> 7), (int)(e & 127u), t)) sm.tv(e & 127u, e >> 7) = t;
             else failed = true;
         }
         unsigned fm = __ballot_sync(0xffffffffu, failed);
@@ -423,7 +426,7 @@ __device__ __forceinline__ int polar_settle_queue(PolarSmem<R, NT>& sm, const Po
             fm &= fm - 1;
             const unsigned es = __shfl_sync(0xffffffffu, e, src);
             const float t = polar_scan_pair<R, NT>(sm, pc, (int)(es >> 7), (int)(es & 127u), lane);
-            if (lane == 0) sm.tval[es & 127u][es >> 7] = t;
+            if (lane == 0) sm.tv(es & 127u, es >> 7) = t;
         }
     }
     __syncwarp();
