@@ -8,6 +8,9 @@
 #include "train_path.cuh"
 #include <stdlib.h>
 
+#ifndef K1_UNIT
+#define K1_UNIT 1
+#endif
 #ifndef K1_NT
 #define K1_NT 64
 #endif
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(1024) k_gt_setup(GridDev grid, ycr_gt_t gt, As
         ws.chunk_off[BG] = s_k[1023];
         ws.totals[0] = s_c[1023];
         ws.totals[1] = s_k[1023];
+        ws.totals[2] = 0;  // K1's work counter
         if ((int64_t)s_c[1023] > ws.cand_cap) ws.err[0] = 1;
     }
 }
@@ -184,16 +188,26 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
     if (ws.err[0]) return;
     init_raydir<R, NT>(sm, tid);
     int cur_bg = -1;
-    for (int work = blockIdx.x; work < T; work += gridDim.x) {
-        const int bg = ws.chunk_bg[work];
+    // Blocks draw units of K1_UNIT consecutive chunks from a global counter (k_gt_setup zeroes it): chunk
+    // costs vary a lot with the GT's shape, and a static split leaves blocks idle at the end.  The barriers
+    // of the hand-out also order the contour reload against the other warp's use of the previous contour.
+    __shared__ int s_unit;
+    for (;;) {
         __syncthreads();
+        if (tid == 0) s_unit = atomicAdd(&ws.totals[2], 1);
+        __syncthreads();
+        const int unit = s_unit;
+        if (unit * K1_UNIT >= T) break;
+      for (int work = unit * K1_UNIT; work < min(T, (unit + 1) * K1_UNIT); ++work) {
+        const int bg = ws.chunk_bg[work];
         if (bg != cur_bg) {
+            if (work != unit * K1_UNIT) __syncthreads();
             const float* cp = a.gt.coor + (int64_t)bg * a.gt.coor_stride;
             float* dst = reinterpret_cast<float*>(sm.contour);
             for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
             cur_bg = bg;
+            __syncthreads();
         }
-        __syncthreads();
         const int c = (work - ws.chunk_off[bg]) * NT + tid;
         const bool active = c < ws.ncand[bg];
         const int4* rect = ws.rect + bg * YCR_MAX_LEVELS;
@@ -240,6 +254,7 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             ws.cand_ov[m] = ov;
             ws.cand_align[m] = align_of(score, ov, a.cfg.alpha, a.cfg.beta);
         }
+      }
     }
 }
 
@@ -634,7 +649,7 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
     w.chunk_bg = al.take<int>(chunks_cap);
     w.chunks_cap = (int)chunks_cap;
     w.valid = al.take<uint8_t>(BG + 1);
-    w.totals = al.take<int>(2);
+    w.totals = al.take<int>(4);
     w.err = al.take<int>(1);
     w.cand_align = al.take<float>((size_t)cand_cap + 1);
     w.cand_ov = al.take<float>((size_t)cand_cap + 1);

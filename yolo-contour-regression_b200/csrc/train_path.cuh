@@ -13,7 +13,7 @@ struct AssignWs {
     int* chunk_bg;     // [chunks_cap] GT of every chunk (saves the per-chunk binary search in K1)
     int chunks_cap;
     uint8_t* valid;    // [BG]
-    int* totals;       // [2] = {M, T}
+    int* totals;       // [4] = {M, T, K1 work counter, -}
     int* err;          // [1] device error flag (candidate capacity exceeded)
     // K1: per-candidate metrics
     float* cand_align; // [cap]
