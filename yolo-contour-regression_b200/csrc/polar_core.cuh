@@ -28,6 +28,14 @@
 #ifndef YCR_GROUP
 #define YCR_GROUP 4   // contour points fetched / inserted / stored together in the sweep
 #endif
+#ifndef YCR_FWD
+#define YCR_FWD 2     // points of a group whose list updates are forwarded in registers
+#endif
+#define YCR_STR(x) #x
+#define YCR_UNROLL(n) _Pragma(YCR_STR(unroll n))
+#ifndef YCR_OWN_UNROLL
+#define YCR_OWN_UNROLL 4
+#endif
 #define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
 #define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
 
@@ -61,6 +69,13 @@ struct PolarSmem {
     __device__ __forceinline__ float& tv(int i, int t) { return reinterpret_cast<float*>(&list[i][t])[3]; }
     __device__ __forceinline__ float tv(int i, int t) const { return reinterpret_cast<const float*>(&list[i][t])[3]; }
 };
+
+// one MUFU.RSQ (the arguments here are squared pixel distances, never denormal)
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // sorted insert with depth-2 dependency: new k_i = max(k_{i-1}, min(k_i, x))
 __device__ __forceinline__ void insert4(uint32_t& k0, uint32_t& k1, uint32_t& k2, uint32_t& k3, uint32_t x) {
@@ -116,18 +131,18 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
     }
     int ray = 0;
     float cr = 1.f, sr = 0.f;
-    const float tan_in = pc.tan_in, ks = pc.key_scale;
+    const float tan_in = pc.tan_in, ks = pc.key_scale, cstep = pc.cos_step, sstep = pc.sin_step;
     for (int j0 = 0; j0 < YCR_C; j0 += YCR_GROUP) {
         // phase 1: everything that does not depend on the current bin, four points at once
         float vx[YCR_GROUP], vy[YCR_GROUP], inv[YCR_GROUP];
 #pragma unroll
         for (int u = 0; u < YCR_GROUP; ++u) {
             const float2 p = sm.contour[j0 + u];
-            vx[u] = p.x - ax;
+            // atan2(0,0) = 0, the direction of ray 0: a point exactly on the anchor gets vx = 1e-18 (any
+            // other difference of coordinates is >= an ulp of a pixel coordinate and absorbs the bias)
+            vx[u] = (p.x - ax) + 1e-18f;
             vy[u] = p.y - ay;
-            float l2 = fmaf(vx[u], vx[u], vy[u] * vy[u]);
-            if (l2 == 0.f) { vx[u] = 1.f; l2 = 1.f; }  // atan2(0,0) = 0: direction of ray 0
-            inv[u] = rsqrtf(l2);
+            inv[u] = rsqrt_fast(fmaf(vx[u], vx[u], vy[u] * vy[u]));
         }
         // phase 2: bin of each of the four points (serial only through the tracked ray) and its key.
         // The usual move - one bin up or down - is branch-free: cross/dot and the ray direction are
@@ -145,14 +160,16 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             float crs = fmaf(vy[u], cr, -vx[u] * sr);
             const bool need = !(fabsf(crs) <= tan_in * dot);
             const bool up = crs >= 0.f;
-            const float sg = up ? pc.sin_step : -pc.sin_step;
-            const float dot2 = fmaf(dot, pc.cos_step, crs * sg);
-            const float crs2 = fmaf(crs, pc.cos_step, -dot * sg);
-            const float cr2 = fmaf(cr, pc.cos_step, -sr * sg);
-            const float sr2 = fmaf(sr, pc.cos_step, cr * sg);
-            int ray2 = ray + (up ? 1 : -1);
-            ray2 = (ray2 < 0) ? ray2 + R : ((ray2 >= R) ? ray2 - R : ray2);
-            if (need) { ray = ray2; dot = dot2; crs = crs2; cr = cr2; sr = sr2; }
+            // rotate by zero (exact: x*1 + y*0) or by one ray spacing towards the point
+            const float rc = need ? cstep : 1.f;
+            const float rs = need ? (up ? sstep : -sstep) : 0.f;
+            const float dot2 = fmaf(dot, rc, crs * rs);
+            const float crs2 = fmaf(crs, rc, -dot * rs);
+            const float cr2 = fmaf(cr, rc, -sr * rs);
+            const float sr2 = fmaf(sr, rc, cr * rs);
+            dot = dot2; crs = crs2; cr = cr2; sr = sr2;
+            ray += need ? (up ? 1 : -1) : 0;
+            ray = (ray < 0) ? R - 1 : ((ray >= R) ? 0 : ray);
             if (!(fabsf(crs) <= tan_in * dot)) {  // more than one bin away (sparse side / jump): walk, exactly
                 const int dir = up ? 1 : -1;
                 int guard = 0;
@@ -169,29 +186,32 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             const float key = fabsf(crs) * inv[u];
             pk[u] = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
         }
-        // phase 3: the four lists and counts are fetched together ...
-        uint4 L[YCR_GROUP];
-        unsigned c[YCR_GROUP];
+        // phases 3-5, per sub-group of YCR_FWD points: the lists and counts are fetched together, updated in
+        // contour order - forwarding the result of an earlier point of the same bin (the usual case) instead
+        // of going through shared memory again - and written back in order (a later store to the same bin
+        // carries all updates).  Sub-groups follow each other through shared memory.
 #pragma unroll
-        for (int u = 0; u < YCR_GROUP; ++u) {
-            L[u] = sm.list[rb[u]][tid];
-            c[u] = sm.cnt[rb[u]][tid];
-        }
-        // phase 4: ... updated in contour order, forwarding the result of an earlier point of the same
-        // bin (the usual case) instead of going through shared memory again ...
+        for (int u0 = 0; u0 < YCR_GROUP; u0 += YCR_FWD) {
+            uint4 L[YCR_FWD];
+            unsigned c[YCR_FWD];
 #pragma unroll
-        for (int u = 0; u < YCR_GROUP; ++u) {
+            for (int u = 0; u < YCR_FWD; ++u) {
+                L[u] = sm.list[rb[u0 + u]][tid];
+                c[u] = sm.cnt[rb[u0 + u]][tid];
+            }
 #pragma unroll
-            for (int w = 0; w < u; ++w)
-                if (rb[w] == rb[u]) { L[u] = L[w]; c[u] = c[w]; }
-            insert4(L[u].x, L[u].y, L[u].z, L[u].w, pk[u]);
-            c[u] = min(255u, c[u] + 1u);
-        }
-        // phase 5: ... and written back in order (a later store to the same bin carries all updates)
+            for (int u = 0; u < YCR_FWD; ++u) {
 #pragma unroll
-        for (int u = 0; u < YCR_GROUP; ++u) {
-            sm.list[rb[u]][tid] = L[u];
-            sm.cnt[rb[u]][tid] = (unsigned char)c[u];
+                for (int w = 0; w < u; ++w)
+                    if (rb[u0 + w] == rb[u0 + u]) { L[u] = L[w]; c[u] = c[w]; }
+                insert4(L[u].x, L[u].y, L[u].z, L[u].w, pk[u0 + u]);
+                c[u] = min(255u, c[u] + 1u);
+            }
+#pragma unroll
+            for (int u = 0; u < YCR_FWD; ++u) {
+                sm.list[rb[u0 + u]][tid] = L[u];
+                sm.cnt[rb[u0 + u]][tid] = (unsigned char)c[u];
+            }
         }
     }
     sm.anchor[tid] = make_float2(ax, ay);
@@ -215,6 +235,7 @@ __device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, cons
     const float2 a = sm.anchor[owner];
     const float2 cs = sm.raydir[ray];
     uint4 K = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
+#pragma unroll 1
     for (int j = 0; j < YCR_C; ++j) {
         const float2 p = sm.contour[j];
         float vx = p.x - a.x;
@@ -236,6 +257,7 @@ __device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const Pola
     const unsigned lane = threadIdx.x & 31u;
     unsigned short* wq = sm.queue[tid >> 5];
     int nq = 0;
+YCR_UNROLL(YCR_OWN_UNROLL)
     for (int i = 0; i < R; ++i) {
         bool unsettled = false;
         if (active) {
@@ -261,9 +283,7 @@ __device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const Pola
                 if (slot < 16 * R) {
                     wq[slot] = (unsigned short)((tid << 7) | i);
                 } else {  // queue full (pathological warp): settle right here, serially
-                    float t;
-                    if (!polar_settle_pair<R, NT>(sm, pc, tid, i, t)) t = polar_scan_serial<R, NT>(sm, pc, tid, i);
-                    sm.tv(i, tid) = t;
+                    sm.tv(i, tid) = polar_scan_serial<R, NT>(sm, pc, tid, i);
                 }
             }
             nq += __popc(ball);
