@@ -8,11 +8,11 @@
 #include "train_path.cuh"
 #include <stdlib.h>
 
-#ifndef K1_UNIT
-#define K1_UNIT 1
-#endif
 #ifndef K1_NT
 #define K1_NT 64
+#endif
+#ifndef K1_SHARE_QUEUES
+#define K1_SHARE_QUEUES 1
 #endif
 #define K3_NT 512
 #define K4_NT 32   // positives per GT are ~topk: one warp per block
@@ -183,67 +183,111 @@ template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
+    // chunk descriptor of the current iteration: [0] first chunk of the GT, [1] its candidate count,
+    // [2] chunk index, [3] GT index, [4..] the GT's candidate rectangles (int4 per level)
+    __shared__ __align__(16) int s_desc[4 + 4 * YCR_MAX_LEVELS];
+    __shared__ int s_ctl[6];   // queue sharing between the two warps (polar_settle_queue_shared)
+    static_assert(4 + 4 * YCR_MAX_LEVELS <= 32, "descriptor is fetched by one warp, one word per lane");
+    constexpr int CW = (2 * YCR_C + 31) / 32;   // contour words per lane of warp 0
     const int tid = threadIdx.x;
     const int T = ws.totals[1];
     if (ws.err[0]) return;
     init_raydir<R, NT>(sm, tid);
-    int cur_bg = -1;
-    // Blocks draw units of K1_UNIT consecutive chunks from a global counter (k_gt_setup zeroes it): chunk
-    // costs vary a lot with the GT's shape, and a static split leaves blocks idle at the end.  The barriers
-    // of the hand-out also order the contour reload against the other warp's use of the previous contour.
-    __shared__ int s_unit;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_unit = atomicAdd(&ws.totals[2], 1);
-        __syncthreads();
-        const int unit = s_unit;
-        if (unit * K1_UNIT >= T) break;
-      for (int work = unit * K1_UNIT; work < min(T, (unit + 1) * K1_UNIT); ++work) {
-        const int bg = ws.chunk_bg[work];
-        if (bg != cur_bg) {
-            if (work != unit * K1_UNIT) __syncthreads();
-            const float* cp = a.gt.coor + (int64_t)bg * a.gt.coor_stride;
-            float* dst = reinterpret_cast<float*>(sm.contour);
-            for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
-            cur_bg = bg;
-            __syncthreads();
+
+    // Blocks draw chunks from a global counter (k_gt_setup zeroes it): chunk costs vary a lot with the GT's
+    // shape, and a static split leaves blocks idle at the end.  Warp 0 runs one chunk ahead: it draws the
+    // next chunk before the sweep and fetches that chunk's descriptor and contour into registers after it,
+    // so the loads are in flight during the settlement and land in shared memory at the next barrier.
+    int n_work = T, n_bg = -1, n_desc = 0;
+    float n_contour[CW];
+    auto fetch_next = [&](int drawn) {          // warp 0, all lanes; `drawn` valid in lane 0
+        n_work = __shfl_sync(0xffffffffu, drawn, 0);
+        n_bg = -1;
+        if (n_work < T) {
+            int bgl = 0;
+            if (tid == 0) bgl = ws.chunk_bg[n_work];
+            n_bg = __shfl_sync(0xffffffffu, bgl, 0);
+            const float* cp = a.gt.coor + (int64_t)n_bg * a.gt.coor_stride;
+#pragma unroll
+            for (int k = 0; k < CW; ++k)
+                if (k * 32 + tid < 2 * YCR_C) n_contour[k] = cp[k * 32 + tid];
+            if (tid == 0) n_desc = ws.chunk_off[n_bg];
+            else if (tid == 1) n_desc = ws.ncand[n_bg];
+            else if (tid == 2) n_desc = n_work;
+            else if (tid == 3) n_desc = n_bg;
+            else if (tid < 4 + 4 * YCR_MAX_LEVELS)
+                n_desc = reinterpret_cast<const int*>(ws.rect)[n_bg * 4 * YCR_MAX_LEVELS + tid - 4];
+        } else if (tid == 2) {
+            n_desc = T;
         }
-        const int c = (work - ws.chunk_off[bg]) * NT + tid;
-        const bool active = c < ws.ncand[bg];
-        const int4* rect = ws.rect + bg * YCR_MAX_LEVELS;
+    };
+    if (tid < 32) {
+        int drawn = 0;
+        if (tid == 0) drawn = atomicAdd(&ws.totals[2], 1);
+        fetch_next(drawn);
+    }
+    for (;;) {
+        __syncthreads();   // both warps are done with the previous chunk's contour and descriptor
+        if (tid < 32) {
+            if (n_bg >= 0) {
+                float* dst = reinterpret_cast<float*>(sm.contour);
+#pragma unroll
+                for (int k = 0; k < CW; ++k)
+                    if (k * 32 + tid < 2 * YCR_C) dst[k * 32 + tid] = n_contour[k];
+            }
+            if (tid < 4 + 4 * YCR_MAX_LEVELS) s_desc[tid] = n_desc;
+            if (tid < 6) s_ctl[tid] = (tid < 2) ? -1 : 0;
+        }
+        __syncthreads();
+        const int work = s_desc[2];
+        if (work >= T) break;
+        const int bg = s_desc[3];
+        int drawn = 0;
+        if (tid == 0) drawn = atomicAdd(&ws.totals[2], 1);   // consumed after the sweep
+        const int c = (work - s_desc[0]) * NT + tid;
+        const int ncand = s_desc[1];
+        const bool active = c < ncand;
         AnchorPos ap{0, 0, 0, 0};
         float ax = 0.f, ay = 0.f;
+        // the candidate's predicted rays and class score are requested now and used after the settlement
+        float pr[R];
+        float score = 0.f;
         if (active) {
-            ap = cand_anchor(a.grid, rect, c);
+            ap = cand_anchor(a.grid, reinterpret_cast<const int4*>(&s_desc[4]), c);
             ax = anchor_coord(ap.ix, a.grid.stride[ap.level]);
             ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
-            polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
-        }
-        const int nq = polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
-        const int nscan = polar_settle_queue<R, NT>(sm, a.pc, tid, nq);
-        if ((tid & 31) == 0) {
-            atomicAdd(&g_ycr_stats[0], (unsigned long long)max(0, min(32, ws.ncand[bg] - (work - ws.chunk_off[bg]) * NT - (tid & ~31))));
-            atomicAdd(&g_ycr_stats[1], (unsigned long long)nq);
-            atomicAdd(&g_ycr_stats[2], (unsigned long long)nscan);
-        }
-        if (active) {
             const int b = bg / a.gt.G;
             const int l = ap.level;
             const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
             const int64_t sc = a.pred.rays_sc[l];
-            const float rs = a.pred.ray_scale[l];
+#pragma unroll
+            for (int i = 0; i < R; ++i) pr[i] = rp[i * sc];
+            const int label = (int)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
+            score = a.pred.cls[l][(int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
+                                  (int64_t)label * a.pred.cls_sc[l]];
+            polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
+        }
+        if (tid < 32) fetch_next(drawn);
+        const int nq = polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        int nscan;
+        if constexpr (NT == 64 && K1_SHARE_QUEUES) nscan = polar_settle_queue_shared<R, NT>(sm, a.pc, tid, nq, s_ctl);
+        else nscan = polar_settle_queue<R, NT>(sm, a.pc, tid, nq);
+        if ((tid & 31) == 0) {
+            atomicAdd(&g_ycr_stats[0], (unsigned long long)max(0, min(32, ncand - (work - s_desc[0]) * NT - (tid & ~31))));
+            atomicAdd(&g_ycr_stats[1], (unsigned long long)nq);
+            atomicAdd(&g_ycr_stats[2], (unsigned long long)nscan);
+        }
+        if (active) {
+            const float rs = a.pred.ray_scale[ap.level];
             float smin = 0.f, smax = 0.f;
-#pragma unroll 4
+#pragma unroll
             for (int i = 0; i < R; ++i) {
-                const float p = rp[i * sc] * rs;
+                const float p = pr[i] * rs;
                 const float t = sm.tv(i, tid);
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
             const float ov = smin / smax;
-            const int label = (int)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
-            float score = a.pred.cls[l][(int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
-                                        (int64_t)label * a.pred.cls_sc[l]];
             if (a.pred.cls_is_logit) score = 1.f / (1.f + expf(-score));
             if (ws.cand_t) {
                 float* tp = ws.cand_t + (int64_t)work * R * NT + tid;
@@ -254,7 +298,6 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             ws.cand_ov[m] = ov;
             ws.cand_align[m] = align_of(score, ov, a.cfg.alpha, a.cfg.beta);
         }
-      }
     }
 }
 

@@ -33,8 +33,11 @@
 #endif
 #define YCR_STR(x) #x
 #define YCR_UNROLL(n) _Pragma(YCR_STR(unroll n))
+#ifndef YCR_STREAMS
+#define YCR_STREAMS 1   // independent ray trackers per thread (arcs of the contour swept in parallel; 1 measured best)
+#endif
 #ifndef YCR_OWN_UNROLL
-#define YCR_OWN_UNROLL 4
+#define YCR_OWN_UNROLL 2
 #endif
 #define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
 #define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
@@ -129,62 +132,71 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
         sm.list[i][tid] = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
         sm.cnt[i][tid] = 0;
     }
-    int ray = 0;
-    float cr = 1.f, sr = 0.f;
+    // YCR_STREAMS independent trackers walk disjoint arcs of the contour (arc s starts at point s*C/S), so a
+    // group holds S short serial chains instead of one long one; insertion order is irrelevant to the lists.
+    constexpr int NS = YCR_STREAMS, PPS = YCR_GROUP / NS, SEG = YCR_C / NS;
+    static_assert(YCR_GROUP % NS == 0 && YCR_C % NS == 0 && SEG % PPS == 0 && PPS % YCR_FWD == 0, "stream layout");
+    int ray[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) ray[s] = 0;
     const float tan_in = pc.tan_in, ks = pc.key_scale, cstep = pc.cos_step, sstep = pc.sin_step;
-    for (int j0 = 0; j0 < YCR_C; j0 += YCR_GROUP) {
+    for (int j0 = 0; j0 < SEG; j0 += PPS) {
         // phase 1: everything that does not depend on the current bin, four points at once
         float vx[YCR_GROUP], vy[YCR_GROUP], inv[YCR_GROUP];
 #pragma unroll
         for (int u = 0; u < YCR_GROUP; ++u) {
-            const float2 p = sm.contour[j0 + u];
+            const float2 p = sm.contour[(u / PPS) * SEG + j0 + (u % PPS)];
             // atan2(0,0) = 0, the direction of ray 0: a point exactly on the anchor gets vx = 1e-18 (any
             // other difference of coordinates is >= an ulp of a pixel coordinate and absorbs the bias)
             vx[u] = (p.x - ax) + 1e-18f;
             vy[u] = p.y - ay;
             inv[u] = rsqrt_fast(fmaf(vx[u], vx[u], vy[u] * vy[u]));
         }
-        // phase 2: bin of each of the four points (serial only through the tracked ray) and its key.
+        // phase 2: bin of each point (serial only through the tracked ray of its stream) and its key.
         // The usual move - one bin up or down - is branch-free: cross/dot and the ray direction are
         // rotated by one ray spacing in registers; the exact direction is reloaded from the table at
-        // the start of every group, so at most four rotations (a few 1e-6 deg) ever accumulate.
+        // the start of every group, so at most PPS rotations (a few 1e-6 deg) ever accumulate.
         int rb[YCR_GROUP];
         uint32_t pk[YCR_GROUP];
-        {
-            const float2 cs = sm.raydir[ray];
-            cr = cs.x; sr = cs.y;
-        }
 #pragma unroll
-        for (int u = 0; u < YCR_GROUP; ++u) {
-            float dot = fmaf(vx[u], cr, vy[u] * sr);
-            float crs = fmaf(vy[u], cr, -vx[u] * sr);
-            const bool need = !(fabsf(crs) <= tan_in * dot);
-            const bool up = crs >= 0.f;
-            // rotate by zero (exact: x*1 + y*0) or by one ray spacing towards the point
-            const float rc = need ? cstep : 1.f;
-            const float rs = need ? (up ? sstep : -sstep) : 0.f;
-            const float dot2 = fmaf(dot, rc, crs * rs);
-            const float crs2 = fmaf(crs, rc, -dot * rs);
-            const float cr2 = fmaf(cr, rc, -sr * rs);
-            const float sr2 = fmaf(sr, rc, cr * rs);
-            dot = dot2; crs = crs2; cr = cr2; sr = sr2;
-            ray += need ? (up ? 1 : -1) : 0;
-            ray = (ray < 0) ? R - 1 : ((ray >= R) ? 0 : ray);
-            if (!(fabsf(crs) <= tan_in * dot)) {  // more than one bin away (sparse side / jump): walk, exactly
-                const int dir = up ? 1 : -1;
-                int guard = 0;
-                do {
-                    ray += dir;
-                    ray = (ray < 0) ? ray + R : ((ray >= R) ? ray - R : ray);
-                    const float2 cs = sm.raydir[ray];
-                    cr = cs.x; sr = cs.y;
-                    dot = fmaf(vx[u], cr, vy[u] * sr);
-                    crs = fmaf(vy[u], cr, -vx[u] * sr);
-                } while (!(fabsf(crs) <= tan_in * dot) && ++guard < R);
+        for (int s = 0; s < NS; ++s) {
+            int ry = ray[s];
+            const float2 cs0 = sm.raydir[ry];
+            float cr = cs0.x, sr = cs0.y;
+#pragma unroll
+            for (int k = 0; k < PPS; ++k) {
+                const int u = s * PPS + k;
+                float dot = fmaf(vx[u], cr, vy[u] * sr);
+                float crs = fmaf(vy[u], cr, -vx[u] * sr);
+                const bool need = !(fabsf(crs) <= tan_in * dot);
+                const bool up = crs >= 0.f;
+                // rotate by zero (exact: x*1 + y*0) or by one ray spacing towards the point
+                const float rc = need ? cstep : 1.f;
+                const float rs = need ? (up ? sstep : -sstep) : 0.f;
+                const float dot2 = fmaf(dot, rc, crs * rs);
+                const float crs2 = fmaf(crs, rc, -dot * rs);
+                const float cr2 = fmaf(cr, rc, -sr * rs);
+                const float sr2 = fmaf(sr, rc, cr * rs);
+                dot = dot2; crs = crs2; cr = cr2; sr = sr2;
+                ry += need ? (up ? 1 : -1) : 0;
+                ry = (ry < 0) ? R - 1 : ((ry >= R) ? 0 : ry);
+                if (!(fabsf(crs) <= tan_in * dot)) {  // more than one bin away (sparse side / jump): walk, exactly
+                    const int dir = up ? 1 : -1;
+                    int guard = 0;
+                    do {
+                        ry += dir;
+                        ry = (ry < 0) ? ry + R : ((ry >= R) ? ry - R : ry);
+                        const float2 cs = sm.raydir[ry];
+                        cr = cs.x; sr = cs.y;
+                        dot = fmaf(vx[u], cr, vy[u] * sr);
+                        crs = fmaf(vy[u], cr, -vx[u] * sr);
+                    } while (!(fabsf(crs) <= tan_in * dot) && ++guard < R);
+                }
+                rb[u] = ry;
+                const float key = fabsf(crs) * inv[u];
+                pk[u] = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(s * SEG + j0 + k);
             }
-            rb[u] = ray;
-            const float key = fabsf(crs) * inv[u];
-            pk[u] = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(j0 + u);
+            ray[s] = ry;
         }
         // phases 3-5, per sub-group of YCR_FWD points: the lists and counts are fetched together, updated in
         // contour order - forwarding the result of an earlier point of the same bin (the usual case) instead
@@ -424,31 +436,84 @@ __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, con
 // be certified is scanned exactly by the whole warp right away.  No block barrier.  Returns the number of
 // exact scans (statistics).
 template <int R, int NT>
+__device__ __forceinline__ int polar_settle_batch(PolarSmem<R, NT>& sm, const PolarConst& pc, const unsigned short* wq,
+                                                  int q0, int nq, unsigned lane) {
+    const int q = q0 + (int)lane;
+    unsigned e = 0;
+    bool failed = false;
+    if (q < nq) {
+        e = wq[q];
+        float t;
+        if (polar_settle_pair<R, NT>(sm, pc, (int)(e >> 7), (int)(e & 127u), t)) sm.tv(e & 127u, e >> 7) = t;
+        else failed = true;
+    }
+    unsigned fm = __ballot_sync(0xffffffffu, failed);
+    const int nscan = __popc(fm);
+    while (fm) {
+        const int src = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const unsigned es = __shfl_sync(0xffffffffu, e, src);
+        const float t = polar_scan_pair<R, NT>(sm, pc, (int)(es >> 7), (int)(es & 127u), lane);
+        if (lane == 0) sm.tv(es & 127u, es >> 7) = t;
+    }
+    return nscan;
+}
+
+template <int R, int NT>
 __device__ __forceinline__ int polar_settle_queue(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, int nq) {
     const unsigned lane = tid & 31u;
     const unsigned short* wq = sm.queue[tid >> 5];
     int nscan = 0;
     __syncwarp();
-    for (int q0 = 0; q0 < nq; q0 += 32) {
-        const int q = q0 + (int)lane;
-        unsigned e = 0;
-        bool failed = false;
-        if (q < nq) {
-            e = wq[q];
-            float t;
-            if (polar_settle_pair<R, NT>(sm, pc, (int)(e >> 7), (int)(e & 127u), t)) sm.tv(e & 127u, e >> 7) = t;
-            else failed = true;
+    for (int q0 = 0; q0 < nq; q0 += 32) nscan += polar_settle_batch<R, NT>(sm, pc, wq, q0, nq, lane);
+    __syncwarp();
+    return nscan;
+}
+
+// Block-shared form for two-warp blocks: a warp that runs out of own pairs takes batches of the other
+// warp's queue (queue lengths differ a lot between the two halves of a chunk).  ctl, per warp w:
+// ctl[w] = published queue length (-1 until the warp's own-bin settlement is complete), ctl[2 + w] = next
+// unclaimed entry, ctl[4 + w] = entries completed.  The caller resets ctl behind a block barrier.
+// On return every pair of THIS warp's queue is settled, whoever did it.
+template <int R, int NT>
+__device__ __forceinline__ int polar_settle_queue_shared(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, int nq,
+                                                         volatile int* ctl) {
+    static_assert(NT == 64, "two warps");
+    const unsigned lane = tid & 31u;
+    const int w = tid >> 5;
+    int nscan = 0;
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();   // lists, counts, anchors, queue entries before the published length
+        ctl[w] = nq;
+    }
+    __syncwarp();
+    for (int turn = 0; turn < 2; ++turn) {
+        const int qw = w ^ turn;
+        int n = nq;
+        if (turn == 1) {
+            // every lane polls (uniform control flow; the value changes once, from -1 to the length)
+            while ((n = ctl[qw]) < 0) __nanosleep(100);
+            __threadfence_block();
+            __syncwarp();
         }
-        unsigned fm = __ballot_sync(0xffffffffu, failed);
-        nscan += __popc(fm);
-        while (fm) {
-            const int src = __ffs(fm) - 1;
-            fm &= fm - 1;
-            const unsigned es = __shfl_sync(0xffffffffu, e, src);
-            const float t = polar_scan_pair<R, NT>(sm, pc, (int)(es >> 7), (int)(es & 127u), lane);
-            if (lane == 0) sm.tv(es & 127u, es >> 7) = t;
+        const unsigned short* wq = sm.queue[qw];
+        for (;;) {
+            int q0 = 0;
+            if (lane == 0) q0 = atomicAdd(const_cast<int*>(&ctl[2 + qw]), 32);
+            q0 = __shfl_sync(0xffffffffu, q0, 0);
+            if (q0 >= n) break;
+            nscan += polar_settle_batch<R, NT>(sm, pc, wq, q0, n, lane);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();   // results before the completion count
+                atomicAdd(const_cast<int*>(&ctl[4 + qw]), min(32, n - q0));
+            }
+            __syncwarp();
         }
     }
+    while (ctl[4 + w] < nq) __nanosleep(100);
+    __threadfence_block();
     __syncwarp();
     return nscan;
 }
