@@ -40,7 +40,7 @@ int launch_bbox_loss(const float* pred_dist, const float* pred_bboxes, const flo
                      const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* tss_d,
                      int B, int A, int nc, int reg_max, int use_dfl, float* loss_out, float* grad_dist, float* grad_bboxes,
                      void* workspace, size_t workspace_bytes, cudaStream_t st);
-int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st);
+int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* scale, cudaStream_t st);
 int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
                         cudaStream_t st);
 int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, cudaStream_t st);
@@ -140,8 +140,8 @@ int ycr_assign(const ycr_grid_t* grid, const ycr_pred_view_t* pred, const ycr_gt
     AssignWs ws;
     const size_t need = assign_ws_layout(&ws, workspace, a.grid, gt->B, gt->G, cfg->topk, cfg->rays, cand_capacity, false);
     if (need > workspace_bytes) { ycr_set_error("assign workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
-    if ((rc = launch_assign_core(a, ws, st))) return rc;
-    if ((rc = launch_positive_targets(a, ws, out->gt_dist, out->centerness, out->pos_capacity, out->n_pos_d, false, nullptr, st))) return rc;
+    if ((rc = launch_assign_core(a, ws, out->n_pos_d, st))) return rc;
+    if ((rc = launch_positive_targets(a, ws, out->gt_dist, out->centerness, out->pos_capacity, false, nullptr, st))) return rc;
     return launch_assign_dense(a, ws, *out, st);
 }
 
@@ -171,19 +171,18 @@ int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, floa
     AssignWs ws;
     const size_t need = assign_ws_layout(&ws, workspace, a.grid, gt->B, gt->G, acfg->topk, R, cand_capacity, true);
     if (need > workspace_bytes) { ycr_set_error("loss workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
-    if ((rc = launch_assign_core(a, ws, st))) return rc;
-    if ((rc = launch_positive_targets(a, ws, nullptr, nullptr, 0, nullptr, true, lcfg, st))) return rc;
+    if ((rc = launch_assign_core(a, ws, nullptr, st))) return rc;
+    if ((rc = launch_positive_targets(a, ws, nullptr, nullptr, 0, true, lcfg, st))) return rc;
     return launch_loss_stream(a, ws, feats, grad_feats, *lcfg, loss_out, st);
 }
 
 int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* grad_feats, const float* scale_d, void* stream) {
     if (!grid || !grad_feats || !scale_d) { ycr_set_error("null argument"); return YCR_E_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    for (int l = 0; l < grid->n_levels; ++l) {
-        int rc = launch_scale(grad_feats[l], (int64_t)B * channels * grid->h[l] * grid->w[l], scale_d, st);
-        if (rc) return rc;
-    }
-    return YCR_OK;
+    int64_t n[YCR_MAX_LEVELS] = {0};
+    if (grid->n_levels > YCR_MAX_LEVELS) { ycr_set_error("too many levels"); return YCR_E_ARG; }
+    for (int l = 0; l < grid->n_levels; ++l) n[l] = (int64_t)B * channels * grid->h[l] * grid->w[l];
+    return launch_scale(grad_feats, n, grid->n_levels, scale_d, st);
 }
 
 int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,

@@ -99,63 +99,77 @@ __device__ __forceinline__ void axis_range(float lo_edge, float hi_edge, float s
     count = max(0, hi - lo + 1);
 }
 
+// One block; GT i of each round of 1024 is handled by thread i, the running candidate / chunk offsets are a
+// block-wide exclusive scan (warp shuffles + one shared array) carried from round to round.
 __global__ void __launch_bounds__(1024) k_gt_setup(GridDev grid, ycr_gt_t gt, AssignWs ws, int chunk) {
-    __shared__ int s_c[1024], s_k[1024];
+    __shared__ int s_wc[32], s_wk[32];
+    __shared__ int s_carry[2];
     const int BG = gt.B * gt.G;
-    const int per = (BG + 1023) / 1024;
-    const int t = threadIdx.x;
-    const int b0 = min(BG, t * per), b1 = min(BG, (t + 1) * per);
-    int sum_c = 0, sum_k = 0;
-    for (int bg = b0; bg < b1; ++bg) {
-        const float* bx = gt.boxes + (int64_t)bg * gt.boxes_stride;
-        const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
-        bool valid = gt.mask_gt ? (gt.mask_gt[(int64_t)bg * gt.mask_stride] != 0.f) : ((x1 + y1 + x2 + y2) > 0.f);
-        int n = 0;
-        for (int l = 0; l < grid.n_levels; ++l) {
-            int fx = 0, cx = 0, fy = 0, cy = 0;
-            if (valid) {
-                axis_range(x1, x2, grid.stride[l], grid.w[l], fx, cx);
-                axis_range(y1, y2, grid.stride[l], grid.h[l], fy, cy);
-                if (cx == 0 || cy == 0) cx = cy = 0;
-            }
-            ws.rect[bg * YCR_MAX_LEVELS + l] = make_int4(fx, fy, cx, cy);
-            n += cx * cy;
-        }
-        ws.valid[bg] = valid ? 1 : 0;
-        ws.ncand[bg] = n;
-        sum_c += n;
-        sum_k += (n + chunk - 1) / chunk;
-    }
-    s_c[t] = sum_c;
-    s_k[t] = sum_k;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) { s_carry[0] = 0; s_carry[1] = 0; }
     __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
-        int vc = 0, vk = 0;
-        if (t >= o) { vc = s_c[t - o]; vk = s_k[t - o]; }
+    for (int base = 0; base < BG; base += 1024) {
+        const int bg = base + t;
+        int n = 0, nk = 0;
+        if (bg < BG) {
+            const float* bx = gt.boxes + (int64_t)bg * gt.boxes_stride;
+            const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+            const bool valid = gt.mask_gt ? (gt.mask_gt[(int64_t)bg * gt.mask_stride] != 0.f) : ((x1 + y1 + x2 + y2) > 0.f);
+            for (int l = 0; l < grid.n_levels; ++l) {
+                int fx = 0, cx = 0, fy = 0, cy = 0;
+                if (valid) {
+                    axis_range(x1, x2, grid.stride[l], grid.w[l], fx, cx);
+                    axis_range(y1, y2, grid.stride[l], grid.h[l], fy, cy);
+                    if (cx == 0 || cy == 0) cx = cy = 0;
+                }
+                ws.rect[bg * YCR_MAX_LEVELS + l] = make_int4(fx, fy, cx, cy);
+                n += cx * cy;
+            }
+            ws.valid[bg] = valid ? 1 : 0;
+            ws.ncand[bg] = n;
+            nk = (n + chunk - 1) / chunk;
+        }
+        // inclusive scans inside the warp, then across the 32 warp totals
+        int ic = n, ik = nk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int vc = __shfl_up_sync(0xffffffffu, ic, o), vk = __shfl_up_sync(0xffffffffu, ik, o);
+            if (lane >= o) { ic += vc; ik += vk; }
+        }
+        if (lane == 31) { s_wc[wid] = ic; s_wk[wid] = ik; }
         __syncthreads();
-        s_c[t] += vc;
-        s_k[t] += vk;
+        if (wid == 0) {
+            int wc = s_wc[lane], wk = s_wk[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int vc = __shfl_up_sync(0xffffffffu, wc, o), vk = __shfl_up_sync(0xffffffffu, wk, o);
+                if (lane >= o) { wc += vc; wk += vk; }
+            }
+            s_wc[lane] = wc;
+            s_wk[lane] = wk;
+        }
+        __syncthreads();
+        const int run_c = s_carry[0] + (wid ? s_wc[wid - 1] : 0) + ic - n;
+        const int run_k = s_carry[1] + (wid ? s_wk[wid - 1] : 0) + ik - nk;
+        if (bg < BG) {
+            ws.cand_off[bg] = run_c;
+            ws.chunk_off[bg] = run_k;
+            for (int k = 0; k < nk; ++k)
+                if (run_k + k < ws.chunks_cap) ws.chunk_bg[run_k + k] = bg;
+        }
+        __syncthreads();
+        if (t == 1023) { s_carry[0] = run_c + n; s_carry[1] = run_k + nk; }
         __syncthreads();
     }
-    int run_c = s_c[t] - sum_c, run_k = s_k[t] - sum_k;
-    for (int bg = b0; bg < b1; ++bg) {
-        ws.cand_off[bg] = run_c;
-        ws.chunk_off[bg] = run_k;
-        const int n = ws.ncand[bg];
-        const int nk = (n + chunk - 1) / chunk;
-        for (int k = 0; k < nk; ++k)
-            if (run_k + k < ws.chunks_cap) ws.chunk_bg[run_k + k] = bg;
-        run_c += n;
-        run_k += nk;
-    }
-    if (t == 1023) {
-        ws.cand_off[BG] = s_c[1023];
-        ws.chunk_off[BG] = s_k[1023];
-        ws.totals[0] = s_c[1023];
-        ws.totals[1] = s_k[1023];
+    if (t == 0) {
+        const int M = s_carry[0], T = s_carry[1];
+        ws.cand_off[BG] = M;
+        ws.chunk_off[BG] = T;
+        ws.totals[0] = M;
+        ws.totals[1] = T;
         ws.totals[2] = 0;  // K1's work counter
-        if ((int64_t)s_c[1023] > ws.cand_cap) ws.err[0] = 1;
+        ws.totals[3] = 0;  // K3's finished-block counter
+        ws.err[0] = ((int64_t)M > ws.cand_cap) ? 1 : 0;
     }
 }
 
@@ -308,7 +322,9 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
 // axis pads with zero-metric anchors; with lowest-index tie-breaking an in-box zero-metric candidate
 // is picked iff fewer than (topk - n_pos) zero-metric anchors precede it.
 // ------------------------------------------------------------------------------------------------
+#define K2_CACHE 2048   // align metrics of one GT kept in shared memory (per warp); larger GTs re-read L2
 __global__ void __launch_bounds__(128) k_topk_per_gt(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+    __shared__ float s_al[4][K2_CACHE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bg = blockIdx.x * 4 + warp;
     const int BG = a.gt.B * a.gt.G;
@@ -318,31 +334,62 @@ __global__ void __launch_bounds__(128) k_topk_per_gt(const __grid_constant__ Ass
     const int n = ws.valid[bg] ? ws.ncand[bg] : 0;
     const float* al = ws.cand_align + ws.cand_off[bg];
     const int4* rect = ws.rect + bg * YCR_MAX_LEVELS;
-    float last_v = __int_as_float(0x7f800000);  // +inf
-    int last_c = -1;
     int n_sel = 0;
-    for (int k = 0; k < topk && n > 0; ++k) {
-        float bv = 0.f;
-        int bc = 0x7fffffff;
-        for (int c = lane; c < n; c += 32) {
-            const float v = al[c];
-            const bool elig = (v > 0.f) && (v < last_v || (v == last_v && c > last_c));
-            if (elig && (v > bv)) { bv = v; bc = c; }  // ascending c: first maximum kept
-        }
+    int my_pick = -1;   // lane k keeps the k-th pick (topk <= 32), converted to an anchor index at the end
+    if (n <= K2_CACHE) {
+        // cached form: a picked entry is overwritten with -1, so every pass is a plain arg-max
+        float* s = s_al[warp];
+        for (int c = lane; c < n; c += 32) s[c] = al[c];
+        __syncwarp();
+        for (int k = 0; k < topk && n > 0; ++k) {
+            float bv = 0.f;
+            int bc = 0x7fffffff;
+#pragma unroll 4
+            for (int c = lane; c < n; c += 32) {
+                const float v = s[c];
+                if (v > bv) { bv = v; bc = c; }  // ascending c: first maximum kept
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-            if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            }
+            if (bc == 0x7fffffff) break;
+            if (lane == 0) s[bc] = -1.f;
+            if (topk <= 32) { if (lane == n_sel) my_pick = bc; }
+            else if (lane == 0) { const AnchorPos p = cand_anchor(a.grid, rect, bc); sel[n_sel] = a.grid.off[p.level] + p.a_local; }
+            ++n_sel;
+            __syncwarp();
         }
-        if (bc == 0x7fffffff) break;
-        if (lane == 0) {
-            const AnchorPos p = cand_anchor(a.grid, rect, bc);
-            sel[n_sel] = a.grid.off[p.level] + p.a_local;
+    } else {
+        float last_v = __int_as_float(0x7f800000);  // +inf
+        int last_c = -1;
+        for (int k = 0; k < topk && n > 0; ++k) {
+            float bv = 0.f;
+            int bc = 0x7fffffff;
+            for (int c = lane; c < n; c += 32) {
+                const float v = al[c];
+                const bool elig = (v > 0.f) && (v < last_v || (v == last_v && c > last_c));
+                if (elig && (v > bv)) { bv = v; bc = c; }  // ascending c: first maximum kept
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+                if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            }
+            if (bc == 0x7fffffff) break;
+            if (topk <= 32) { if (lane == n_sel) my_pick = bc; }
+            else if (lane == 0) { const AnchorPos p = cand_anchor(a.grid, rect, bc); sel[n_sel] = a.grid.off[p.level] + p.a_local; }
+            ++n_sel;
+            last_v = bv;
+            last_c = bc;
         }
-        ++n_sel;
-        last_v = bv;
-        last_c = bc;
+    }
+    if (topk <= 32 && lane < n_sel) {
+        const AnchorPos p = cand_anchor(a.grid, rect, my_pick);
+        sel[lane] = a.grid.off[p.level] + p.a_local;
     }
     if (n_sel < topk && n > 0) {
         // zero-metric in-box candidates as topk fillers (rare)
@@ -377,24 +424,32 @@ __global__ void __launch_bounds__(128) k_topk_per_gt(const __grid_constant__ Ass
 // utils/tal.py:214-248), orders the positives (g,a)-lexicographically (utils/tal.py:1175), and
 // computes the normalised target score (utils/tal.py:1197-1202).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+__global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                                         int* n_pos_d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = a.grid.off[YCR_MAX_LEVELS];
     const int G = a.gt.G, topk = a.cfg.topk, pos_cap = ws.pos_cap;
-    uint32_t* s_a = reinterpret_cast<uint32_t*>(smem_raw);          // [A]
+    int4* s_rect = reinterpret_cast<int4*>(smem_raw);               // [G][levels] candidate rectangles of the image's GTs
+    uint32_t* s_a = reinterpret_cast<uint32_t*>(s_rect + G * YCR_MAX_LEVELS);  // [A]
     int* s_pa = reinterpret_cast<int*>(s_a + A);                    // [pos_cap]
     int* s_pg = s_pa + pos_cap;                                     // [pos_cap]
     float* s_al = reinterpret_cast<float*>(s_pg + pos_cap);         // [pos_cap]
-    uint32_t* s_gal = reinterpret_cast<uint32_t*>(s_al + pos_cap);  // [G]
+    int* s_conf = reinterpret_cast<int*>(s_al + pos_cap);           // [pos_cap] anchors picked by several GTs
+    uint32_t* s_gal = reinterpret_cast<uint32_t*>(s_conf + pos_cap);  // [G]
     uint32_t* s_gov = s_gal + G;                                    // [G]
     int* s_gcnt = reinterpret_cast<int*>(s_gov + G);                // [G]
     int* s_gstart = s_gcnt + G;                                     // [G]
-    __shared__ int s_n;
+    int* s_goff = s_gstart + G;                                     // [G] first candidate of the GT, -1 when invalid
+    __shared__ int s_n, s_nc, s_last;
     __shared__ float s_red[32];
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int i = tid; i < A; i += K3_NT) s_a[i] = 0;
-    for (int i = tid; i < G; i += K3_NT) { s_gal[i] = 0; s_gov[i] = 0; s_gcnt[i] = 0; }
-    if (tid == 0) s_n = 0;
+    for (int i = tid; i < G; i += K3_NT) {
+        s_gal[i] = 0; s_gov[i] = 0; s_gcnt[i] = 0;
+        s_goff[i] = ws.valid[b * G + i] ? ws.cand_off[b * G + i] : -1;
+    }
+    for (int i = tid; i < G * YCR_MAX_LEVELS; i += K3_NT) s_rect[i] = ws.rect[b * G * YCR_MAX_LEVELS + i];
+    if (tid == 0) { s_n = 0; s_nc = 0; }
     __syncthreads();
     for (int e = tid; e < G * topk; e += K3_NT) {
         const int g = e / topk;
@@ -407,24 +462,46 @@ __global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__
         const uint32_t v = s_a[an];
         const int cnt = v >> 16;
         pos_row[an] = -1;
-        if (cnt == 0) continue;
-        int g = v & 0xFFFFu;
-        if (cnt > 1) {
+        if (cnt == 1) {
+            const int g = v & 0xFFFFu;
+            const int idx = atomicAdd(&s_n, 1);
+            if (idx < pos_cap) { s_pa[idx] = an; s_pg[idx] = g; }
+            atomicAdd(&s_gcnt[g], 1);
+        } else if (cnt > 1) {
+            const int idx = atomicAdd(&s_nc, 1);
+            if (idx < pos_cap) s_conf[idx] = an;
+        }
+    }
+    __syncthreads();
+    // anchors picked by several GTs: one warp per anchor, lanes over the image's GTs; the GT with the highest
+    // overlap among ALL GTs whose box holds the anchor wins, the lowest index on ties (argmax), GT 0 if none
+    {
+        const int lane = tid & 31, wid = tid >> 5;
+        const int nc = min(s_nc, pos_cap);
+        for (int ci = wid; ci < nc; ci += K3_NT / 32) {
+            const int an = s_conf[ci];
             const AnchorPos p = anchor_pos(a.grid, an);
             float best = 0.f;
-            g = 0;
-            for (int gg = 0; gg < G; ++gg) {
-                const int bg = b * G + gg;
-                if (!ws.valid[bg]) continue;
-                const int ci = cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, p);
-                if (ci < 0) continue;
-                const float ov = ws.cand_ov[ws.cand_off[bg] + ci];
+            int g = 0;
+            for (int gg = lane; gg < G; gg += 32) {
+                if (s_goff[gg] < 0) continue;
+                const int c = cand_index(a.grid, s_rect + gg * YCR_MAX_LEVELS, p);
+                if (c < 0) continue;
+                const float ov = ws.cand_ov[s_goff[gg] + c];
                 if (ov > best) { best = ov; g = gg; }
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int og = __shfl_xor_sync(0xffffffffu, g, o);
+                if (ob > best || (ob == best && og < g)) { best = ob; g = og; }
+            }
+            if (lane == 0) {
+                const int idx = atomicAdd(&s_n, 1);
+                if (idx < pos_cap) { s_pa[idx] = an; s_pg[idx] = g; }
+                atomicAdd(&s_gcnt[g], 1);
+            }
         }
-        const int idx = atomicAdd(&s_n, 1);
-        if (idx < pos_cap) { s_pa[idx] = an; s_pg[idx] = g; }
-        atomicAdd(&s_gcnt[g], 1);
     }
     __syncthreads();
     const int n = min(s_n, pos_cap);
@@ -444,14 +521,14 @@ __global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__
         o_anchor[rank] = an;
         o_g[rank] = g;
         pos_row[an] = rank;
-        const int bg = b * G + g;
         float alv = 0.f, ovv = 0.f;
-        const int ci = ws.valid[bg] ? cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, anchor_pos(a.grid, an)) : -1;
+        const int ci = (s_goff[g] >= 0) ? cand_index(a.grid, s_rect + g * YCR_MAX_LEVELS, anchor_pos(a.grid, an)) : -1;
         if (ci >= 0) {
-            alv = ws.cand_align[ws.cand_off[bg] + ci];
-            ovv = ws.cand_ov[ws.cand_off[bg] + ci];
+            alv = ws.cand_align[s_goff[g] + ci];
+            ovv = ws.cand_ov[s_goff[g] + ci];
         }
         s_al[rank] = alv;
+        s_pg[p] = g;
         atomicMax(&s_gal[g], __float_as_uint(fmaxf(alv, 0.f)));
         atomicMax(&s_gov[g], __float_as_uint(fmaxf(ovv, 0.f)));
     }
@@ -476,18 +553,38 @@ __global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__
         ws.gt_row_start[b * G + g] = s_gstart[g];
         ws.gt_row_cnt[b * G + g] = min(s_gcnt[g], max(0, pos_cap - s_gstart[g]));
     }
-}
-
-// image row bases and the loss normaliser target_scores_sum = max(sum, 1) (utils/loss.py:866)
-__global__ void k_finalize_counts(AssignWs ws, int B, int* img_base, float* tss, int* n_pos_d) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // The last block to finish turns the per-image counts into row bases and the loss normaliser
+    // target_scores_sum = max(sum, 1) (utils/loss.py:866), summed in image order (deterministic).
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&ws.totals[3], 1) == (int)gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (s_last && tid < 32) {
+        __threadfence();
+        const int B = gridDim.x;
         int run = 0;
         double s = 0.0;
-        for (int b = 0; b < B; ++b) { img_base[b] = run; run += ws.npos[b]; s += (double)ws.tss_part[b]; }
-        img_base[B] = run;
-        tss[0] = fmaxf((float)s, 1.f);
-        tss[1] = (float)s;
-        if (n_pos_d) *n_pos_d = ws.err[0] ? -1 : run;  // -1: candidate capacity exceeded, nothing was assigned
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int bb = b0 + tid;
+            const int np = (bb < B) ? __ldcg(&ws.npos[bb]) : 0;
+            const double tp = (bb < B) ? (double)__ldcg(&ws.tss_part[bb]) : 0.0;
+            int inc = np;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (tid >= o) inc += v;
+            }
+            if (bb < B) ws.img_base[bb] = run + inc - np;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+            for (int k = 0; k < min(32, B - b0); ++k) s += __shfl_sync(0xffffffffu, tp, k);
+        }
+        if (tid == 0) {
+            ws.img_base[B] = run;
+            ws.tss[0] = fmaxf((float)s, 1.f);
+            ws.tss[1] = (float)s;
+            if (n_pos_d) *n_pos_d = ws.err[0] ? -1 : run;  // -1: candidate capacity exceeded, nothing was assigned
+            ws.totals[3] = 0;
+        }
     }
 }
 
@@ -496,6 +593,24 @@ __global__ void k_finalize_counts(AssignWs ws, int B, int* img_base, float* tss,
 // for the fused loss, the Polar-IoU log-ratio term of MaskIOULoss (utils/loss.py:113-127) with its
 // gradient with respect to the raw ray outputs.  One block per GT.
 // ------------------------------------------------------------------------------------------------
+// Sum of R terms in the association order of k_positive_gather (lane i % 32 adds its terms in order, then
+// an xor-butterfly 16..1 across the lanes), so that both forms of K4 give bit-identical sums.
+template <int R>
+__device__ __forceinline__ float butterfly_sum(const float (&term)[R]) {
+    float p[32];
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+        p[l] = 0.f;
+#pragma unroll
+        for (int i = l; i < R; i += 32) p[l] += term[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int l = 0; l < o; ++l) p[l] += p[l + o];
+    return p[0];
+}
+
 struct PosArgs {
     float* gt_dist; float* centerness; int pos_capacity;
     const int* img_base; const float* tss;
@@ -550,13 +665,15 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
             const int64_t sc = a.pred.rays_sc[l];
             const float rs = a.pred.ray_scale[l];
-            float smin = 0.f, smax = 0.f;
+            float mn[R], mx[R];
+#pragma unroll
             for (int i = 0; i < R; ++i) {
                 const float p = rp[i * sc] * rs;
                 const float t = sm.tv(i, tid);
-                smin += fmaxf(fminf(p, t), YCR_FLOOR);
-                smax += fmaxf(p, t);
+                mn[i] = fmaxf(fminf(p, t), YCR_FLOOR);
+                mx[i] = fmaxf(p, t);
             }
+            const float smin = butterfly_sum<R>(mn), smax = butterfly_sum<R>(mx);
             const float w = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
             ws.pos_loss[(int64_t)b * ws.pos_cap + row] = logf(smax / smin) * w;
             const float coef = w / pa.tss[0] * pa.box_gain * (float)a.gt.B * rs;
@@ -575,55 +692,73 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
 }
 
 // K4 (gather form): when K1 kept the ray targets of every candidate, a positive's targets are just read
-// back - one thread per positive; same outputs as k_positive_targets.
+// back - one warp per positive, lanes over the rays; same outputs as k_positive_targets.
 template <int R>
-__global__ void __launch_bounds__(128) k_positive_gather(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+__global__ void __launch_bounds__(256) k_positive_gather(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                          const PosArgs pa) {
+    constexpr int NR = (R + 31) / 32;
     const int b = blockIdx.y;
-    const int row = blockIdx.x * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= ws.npos[b]) return;
-    const int an = ws.pos_anchor[(int64_t)b * ws.pos_cap + row];
-    const int g = ws.pos_g[(int64_t)b * ws.pos_cap + row];
+    const int64_t prow = (int64_t)b * ws.pos_cap + row;
+    const int an = ws.pos_anchor[prow];
+    const int g = ws.pos_g[prow];
     const int bg = b * a.gt.G + g;
     const AnchorPos ap = anchor_pos(a.grid, an);
+    const int l = ap.level;
+    // the predictions do not depend on the candidate lookup: request them first
+    const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+    const int64_t sc = a.pred.rays_sc[l];
+    const float rs = a.pred.ray_scale[l];
+    float p[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const int i = lane + 32 * k;
+        p[k] = (pa.with_loss && i < R) ? rp[i * sc] * rs : 0.f;
+    }
+    const float w = ws.pos_norm[prow];
+    const float tss = pa.tss[0];
+    const int grow = pa.img_base[b] + row;
     const int ci = ws.valid[bg] ? cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, ap) : -1;
     const float* tp = nullptr;
     if (ci >= 0) tp = ws.cand_t + ((int64_t)(ws.chunk_off[bg] + ci / K1_NT) * R) * K1_NT + (ci % K1_NT);
-    const int grow = pa.img_base[b] + row;
-    float t[R];
-    float tmin = 3.4e38f, tmax = 0.f;
+    float t[NR];
+    float tmin = 3.4e38f, tmax = 0.f, smin = 0.f, smax = 0.f;
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-        t[i] = tp ? tp[i * K1_NT] : YCR_FLOOR;
-        tmin = fminf(tmin, t[i]);
-        tmax = fmaxf(tmax, t[i]);
-        if (pa.gt_dist && grow < pa.pos_capacity) pa.gt_dist[(int64_t)grow * R + i] = t[i];
-    }
-    if (pa.centerness && grow < pa.pos_capacity) pa.centerness[grow] = sqrtf(tmin / tmax);
-    if (pa.with_loss) {
-        const int l = ap.level;
-        const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
-        const int64_t sc = a.pred.rays_sc[l];
-        const float rs = a.pred.ray_scale[l];
-        float p[R];
-        float smin = 0.f, smax = 0.f;
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-            p[i] = rp[i * sc] * rs;
-            smin += fmaxf(fminf(p[i], t[i]), YCR_FLOOR);
-            smax += fmaxf(p[i], t[i]);
+    for (int k = 0; k < NR; ++k) {
+        const int i = lane + 32 * k;
+        if (i < R) {
+            t[k] = tp ? tp[i * K1_NT] : YCR_FLOOR;
+            tmin = fminf(tmin, t[k]);
+            tmax = fmaxf(tmax, t[k]);
+            smin += fmaxf(fminf(p[k], t[k]), YCR_FLOOR);
+            smax += fmaxf(p[k], t[k]);
+            if (pa.gt_dist && grow < pa.pos_capacity) pa.gt_dist[(int64_t)grow * R + i] = t[k];
         }
-        const float w = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
-        ws.pos_loss[(int64_t)b * ws.pos_cap + row] = logf(smax / smin) * w;
-        const float coef = w / pa.tss[0] * pa.box_gain * (float)a.gt.B * rs;
-        const float imax = 1.f / smax, imin = 1.f / smin;
-        float* gp = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
+    }
 #pragma unroll
-        for (int i = 0; i < R; ++i) {
-            float gr = 0.f;
-            if (p[i] >= t[i]) gr += imax;                       // max() routes to pred (first index on ties)
-            if (p[i] <= t[i] && p[i] >= YCR_FLOOR) gr -= imin;  // min() routes to pred; clamp passes when >= floor
-            gp[i] = gr * coef;
+    for (int o = 16; o > 0; o >>= 1) {   // fixed-shape butterflies: deterministic
+        tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+        tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        smin += __shfl_xor_sync(0xffffffffu, smin, o);
+        smax += __shfl_xor_sync(0xffffffffu, smax, o);
+    }
+    if (lane == 0 && pa.centerness && grow < pa.pos_capacity) pa.centerness[grow] = sqrtf(tmin / tmax);
+    if (pa.with_loss) {
+        if (lane == 0) ws.pos_loss[prow] = logf(smax / smin) * w;
+        const float coef = w / tss * pa.box_gain * (float)a.gt.B * rs;
+        const float imax = 1.f / smax, imin = 1.f / smin;
+        float* gp = ws.pos_grad + prow * R;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            const int i = lane + 32 * k;
+            if (i < R) {
+                float gr = 0.f;
+                if (p[k] >= t[k]) gr += imax;                       // max() routes to pred (first index on ties)
+                if (p[k] <= t[k] && p[k] >= YCR_FLOOR) gr -= imin;  // min() routes to pred; clamp passes when >= floor
+                gp[i] = gr * coef;
+            }
         }
     }
 }
@@ -742,10 +877,13 @@ static int launch_k1(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
     return YCR_OK;
 }
 
-int launch_assign_core(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
+int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cudaStream_t st) {
     const int B = a.gt.B, G = a.gt.G, BG = B * G;
     const int A = a.grid.off[YCR_MAX_LEVELS];
-    YCR_CUDA_CHECK(cudaMemsetAsync(ws.err, 0, sizeof(int), st));
+    if (BG == 0) {  // otherwise k_gt_setup initialises both
+        YCR_CUDA_CHECK(cudaMemsetAsync(ws.err, 0, sizeof(int), st));
+        YCR_CUDA_CHECK(cudaMemsetAsync(ws.totals, 0, 4 * sizeof(int), st));
+    }
     if (BG > 0) {
         { YcrProfScope ps(YCR_T_SETUP, st); k_gt_setup<<<1, 1024, 0, st>>>(a.grid, a.gt, ws, K1_NT); }
         YCR_LAUNCH_CHECK();
@@ -754,28 +892,26 @@ int launch_assign_core(const AssignArgs& a, const AssignWs& ws, cudaStream_t st)
         { YcrProfScope ps(YCR_T_TOPK, st); k_topk_per_gt<<<(BG + 3) / 4, 128, 0, st>>>(a, ws); }
         YCR_LAUNCH_CHECK();
     }
-    const size_t smem3 = (size_t)A * 4 + (size_t)ws.pos_cap * 12 + (size_t)G * 16 + 64;
+    const size_t smem3 = (size_t)G * YCR_MAX_LEVELS * 16 + (size_t)A * 4 + (size_t)ws.pos_cap * 16 + (size_t)G * 20 + 64;
     YCR_CUDA_CHECK(cudaFuncSetAttribute(k_resolve_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    { YcrProfScope ps(YCR_T_RESOLVE, st); k_resolve_image<<<B, K3_NT, smem3, st>>>(a, ws); }
+    { YcrProfScope ps(YCR_T_RESOLVE, st); k_resolve_image<<<B, K3_NT, smem3, st>>>(a, ws, n_pos_d); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
 
 int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_dist, float* centerness,
-                            int pos_capacity, int* n_pos_d, bool with_loss, const ycr_loss_cfg_t* lcfg,
+                            int pos_capacity, bool with_loss, const ycr_loss_cfg_t* lcfg,
                             cudaStream_t st) {
     const int B = a.gt.B, BG = B * a.gt.G;
     int* img_base = ws.img_base;
     float* tss = ws.tss;
-    k_finalize_counts<<<1, 32, 0, st>>>(ws, B, img_base, tss, n_pos_d);
-    YCR_LAUNCH_CHECK();
     PosArgs pa{gt_dist, centerness, pos_capacity, img_base, tss, with_loss ? 1 : 0, lcfg ? lcfg->box_gain : 0.f};
     if (BG == 0) return YCR_OK;
     YcrProfScope ps(YCR_T_POS, st);
     if (ws.cand_t) {
-        dim3 grid((ws.pos_cap + 127) / 128, B);
-        if (a.cfg.rays == 36) k_positive_gather<36><<<grid, 128, 0, st>>>(a, ws, pa);
-        else k_positive_gather<72><<<grid, 128, 0, st>>>(a, ws, pa);
+        dim3 grid((ws.pos_cap + 7) / 8, B);
+        if (a.cfg.rays == 36) k_positive_gather<36><<<grid, 256, 0, st>>>(a, ws, pa);
+        else k_positive_gather<72><<<grid, 256, 0, st>>>(a, ws, pa);
         YCR_LAUNCH_CHECK();
         return YCR_OK;
     }

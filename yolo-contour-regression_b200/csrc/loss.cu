@@ -227,18 +227,23 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* con
 // ------------------------------------------------------------------------------------------------
 // grad *= scale (device scalar); exits at once when the scalar is 1
 // ------------------------------------------------------------------------------------------------
-__global__ void k_scale(float* p, int64_t n, const float* scale) {
+struct ScaleArgs { float* p[YCR_MAX_LEVELS]; int64_t n[YCR_MAX_LEVELS]; int n_levels; };
+
+__global__ void __launch_bounds__(256) k_scale(const ScaleArgs sa, const float* scale) {
     const float s = *scale;
     if (s == 1.f) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] *= s;
+    for (int l = 0; l < sa.n_levels; ++l)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sa.n[l]; i += stride) sa.p[l][i] *= s;
 }
 
-int launch_scale(float* p, int64_t n, const float* scale, cudaStream_t st) {
-    if (n <= 0) return YCR_OK;
-    int blocks = (int)((n + 1023) / 1024);
-    if (blocks > YCR_NUM_SMS * 8) blocks = YCR_NUM_SMS * 8;
-    k_scale<<<blocks, 256, 0, st>>>(p, n, scale);
+int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* scale, cudaStream_t st) {
+    ScaleArgs sa{};
+    sa.n_levels = 0;
+    for (int l = 0; l < n_levels && l < YCR_MAX_LEVELS; ++l)
+        if (n[l] > 0) { sa.p[sa.n_levels] = p[l]; sa.n[sa.n_levels] = n[l]; ++sa.n_levels; }
+    if (sa.n_levels == 0) return YCR_OK;
+    k_scale<<<YCR_NUM_SMS * 2, 256, 0, st>>>(sa, scale);
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }

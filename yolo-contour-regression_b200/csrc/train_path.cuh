@@ -53,10 +53,10 @@ struct AssignArgs {
     PolarConst pc;
 };
 
-int launch_assign_core(const AssignArgs& a, const AssignWs& ws, cudaStream_t st);
+int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cudaStream_t st);
 int launch_assign_dense(const AssignArgs& a, const AssignWs& ws, const ycr_assign_out_t& out, cudaStream_t st);
 int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_dist, float* centerness,
-                            int pos_capacity, int* n_pos_d, bool with_loss, const ycr_loss_cfg_t* lcfg,
+                            int pos_capacity, bool with_loss, const ycr_loss_cfg_t* lcfg,
                             cudaStream_t st);
 int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* const* feats, float* const* grads,
                        const ycr_loss_cfg_t& lcfg, float* loss_out, cudaStream_t st);
