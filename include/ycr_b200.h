@@ -106,6 +106,9 @@ int ycr_version(void);
  * 0 gt_setup, 1 cand_overlaps, 2 topk, 3 resolve, 4 positives, 5 loss_stream, 6 finalize, 7 decode,
  * 8 nms_filter, 9 nms_sort, 10 nms_suppress), the summed milliseconds and launch count (16 entries). */
 int ycr_profile_begin(int max_records);
+/* Restrict the bracketing to the kernel tags whose bit is set (default: all), so that a timed region can
+ * carry the events of its dominant kernel only. */
+int ycr_profile_select(unsigned tag_mask);
 int ycr_profile_end(float* ms_sum_h, int* count_h);
 /* Work counters of the candidate kernel since the last reset (synchronises the device):
  * out_h[0] candidates swept, [1] (candidate,ray) pairs the own angular bin could not settle,

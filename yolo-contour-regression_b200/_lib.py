@@ -62,6 +62,7 @@ EXPORTS = {
     "ycr_last_error": (C.c_char_p, []),
     "ycr_version": (C.c_int, []),
     "ycr_profile_begin": (C.c_int, [C.c_int]),
+    "ycr_profile_select": (C.c_int, [C.c_uint]),
     "ycr_profile_end": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ycr_debug_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "ycr_candidate_bound_h": (C.c_int64, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int]),

@@ -19,9 +19,10 @@ static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_ev;       // pool
 static std::vector<int> g_prof_tag;              // tag of pair k (events 2k, 2k+1)
 static size_t g_prof_used = 0;
+static unsigned g_prof_mask = 0xFFFFFFFFu;
 
 void ycr_prof_mark(int tag, int end, cudaStream_t st) {
-    if (!g_prof_on) return;
+    if (!g_prof_on || !((g_prof_mask >> tag) & 1u)) return;
     if (!end) {
         if (g_prof_used + 2 > g_prof_ev.size()) return;
         g_prof_tag.push_back(tag);
@@ -71,6 +72,11 @@ int ycr_profile_begin(int max_records) {
     g_prof_tag.clear();
     g_prof_used = 0;
     g_prof_on = true;
+    return YCR_OK;
+}
+
+int ycr_profile_select(unsigned tag_mask) {
+    g_prof_mask = tag_mask;
     return YCR_OK;
 }
 
