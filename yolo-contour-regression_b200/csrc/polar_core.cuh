@@ -275,7 +275,16 @@ YCR_UNROLL(YCR_OWN_UNROLL)
         if (active) {
             const uint4 L = sm.list[i][tid];
             const bool own_gate = (L.x == YCR_EMPTY) || ((L.x >> 9) > pc.q_gate);
-            if (own_gate && pc.gate_l1) {
+            constexpr bool kGateL1 = (180.0 / R - YCR_TOL_DEG) > YCR_GATE_DEG;          // == pc.gate_l1
+            constexpr bool kEmpty3 = (3 * 180.0 / R - 3 * YCR_TOL_DEG) > YCR_GATE_DEG;  // == pc.empty3_gate
+            bool gate = own_gate && kGateL1;
+            if (!kGateL1 && kEmpty3 && L.x == YCR_EMPTY) {
+                // bins narrower than the 3 degree gate: an empty own bin between two empty neighbours
+                // certifies it (nothing within 3*hw - 3 TOL > 3 degrees of the ray)
+                const int ip = (i == 0) ? R - 1 : i - 1, in = (i == R - 1) ? 0 : i + 1;
+                gate = (sm.cnt[ip][tid] | sm.cnt[in][tid]) == 0;
+            }
+            if (gate) {
                 sm.tv(i, tid) = YCR_FLOOR;
             } else if (L.w != YCR_EMPTY && (L.w >> 9) < pc.q_res) {
                 // (for hw < 3 deg every in-bin key is below the gate, so the gate cannot fire here)
