@@ -346,3 +346,51 @@ def test_positive_targets_gather_equals_resweep():
     for x, y in zip(a[3], b[3]):
         assert torch.equal(x, y)
     assert rel_err(a[0].cpu(), g["asg_gt_dist"]) < TOL
+
+
+def test_clustered_contour_bin_count_wraps():
+    """300 of the 360 contour points sit on a 3 px segment: from almost every in-box anchor they fall into
+    one angular bin, whose byte-sized point count wraps.  The kernel must notice (the counts no longer add up
+    to 360) and settle the sparse rays by the exact scan; results are checked against the oracle."""
+    from ycr_b200.tal import TaskAlignedAssigner
+    dev = _dev()
+    shapes = [(40, 40), (20, 20), (10, 10)]
+    strides = [8, 16, 32]
+    anc, st = po.make_anchors(shapes, strides)
+    A = anc.shape[0]
+    gen = torch.Generator().manual_seed(77)
+    # square 60..260 traversed by 60 points, plus a dense 3 px run on its right edge
+    t = torch.linspace(0, 1, 61)[:-1]
+    sq = torch.cat([torch.stack([60 + 200 * t[:15] / t[15], torch.full((15,), 60.)], 1),
+                    torch.stack([torch.full((15,), 260.), 60 + 200 * t[:15] / t[15]], 1),
+                    torch.stack([260 - 200 * t[:15] / t[15], torch.full((15,), 260.)], 1),
+                    torch.stack([torch.full((15,), 60.), 260 - 200 * t[:15] / t[15]], 1)], 0)
+    dense = torch.stack([torch.full((300,), 260.) + 0.013 * torch.arange(300) / 300,
+                         150.0 + 3.0 * torch.arange(300) / 300 + 0.0007], 1)
+    contour = torch.cat([sq[:23], dense, sq[23:]], 0)
+    assert contour.shape == (360, 2)
+    contour = contour + 0.01 * torch.rand(360, 2, generator=gen)
+    gc = contour.reshape(1, 1, 720)
+    gb = torch.tensor([[[60., 60., 260.2, 260.]]])
+    scores = torch.rand(1, A, 2, generator=gen) * 0.8 + 0.1
+    prays = torch.rand(1, A, 36, generator=gen) * 150 + 20
+    asg = TaskAlignedAssigner(topk=10, num_classes=2, alpha=0.5, beta=4.0)
+    asg.debug_metrics = True
+    out = asg(scores.to(dev), prays.to(dev), (anc * st).to(dev), torch.zeros(1, 1, 1, device=dev), gb.to(dev),
+              torch.ones(1, 1, 1, device=dev), gc.to(dev), st.to(dev), None, 0, None, grid=(shapes, strides))
+    mp, gd = out[3].cpu(), out[5].cpu()
+    pos = torch.nonzero(mp[0, 0]).flatten()
+    assert pos.numel() == 10 and gd.shape == (10, 36)
+    ref = po.polar_targets((anc * st)[pos], contour[None].expand(10, 360, 2), 36)
+    ok = ~ref["ambiguous"]
+    assert float(ok.float().mean()) > 0.9
+    assert rel_err(gd[ok], ref["t"][ok]) < TOL
+    # the dense overlaps of ALL candidates (every one swept the wrapped bin) against the oracle
+    ov = asg.last_overlaps[0, 0].cpu()
+    cand = torch.nonzero(po.in_box_mask(anc * st, gb)[0, 0]).flatten()
+    sub = cand[torch.linspace(0, cand.numel() - 1, 60).long()]
+    rt = po.polar_targets((anc * st)[sub], contour[None].expand(sub.numel(), 360, 2), 36)
+    clean = ~rt["ambiguous"].any(1)
+    ref_ov = po.polar_iou(prays[0, sub], rt["t"])
+    assert int(clean.sum()) > 30
+    assert rel_err(ov[sub][clean], ref_ov[clean]) < TOL

@@ -528,7 +528,6 @@ __global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__
             ovv = ws.cand_ov[s_goff[g] + ci];
         }
         s_al[rank] = alv;
-        s_pg[p] = g;
         atomicMax(&s_gal[g], __float_as_uint(fmaxf(alv, 0.f)));
         atomicMax(&s_gov[g], __float_as_uint(fmaxf(ovv, 0.f)));
     }

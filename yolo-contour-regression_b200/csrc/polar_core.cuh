@@ -6,16 +6,16 @@
 // sweeps the 360 contour points ONCE (they are broadcast from shared memory to the whole warp):
 //   * a point belongs to the bin of its nearest ray (|delta| <= 180/R deg, decided by a cross/dot
 //     test against the current ray direction - no atan2 anywhere);
-//   * the bin's four nearest points live in registers as packed (23-bit fixed-point |sin delta|,
-//     9-bit point index) keys kept sorted with 7 independent integer min/max per point; they are
-//     spilled to / refilled from a per-thread shared-memory slot only when the sweep enters another
-//     bin, where the exact number of points of the bin left behind is accumulated as well;
+//   * every bin keeps its four nearest points as packed (23-bit fixed-point |sin delta|, 9-bit point
+//     index) keys in a per-thread uint4 slot of shared memory, kept sorted with 7 independent integer
+//     min/max per point, and the exact number of points that fell into it (a byte; a bin that takes
+//     256 points or more is detected through the total);
 //   * after the sweep a ray is settled when its own bin certifies the answer (four points strictly
-//     inside the bin, or nothing within 3 degrees).  The others (sparse side of the contour) are
-//     queued block-wide; a queued pair is settled by evaluating the contour neighbourhoods of the
-//     points its bin did catch, and the result is certified against the per-bin counts (every point of
-//     the bins that could hold a nearer point has been looked at).  What cannot be certified goes to
-//     a second queue that one warp per pair settles by an exact scan of all 360 points.
+//     inside the bin, or nothing within 3 degrees).  The others (sparse side of the contour) go to the
+//     queue of the thread's warp; a queued pair is settled by evaluating the contour neighbourhood of
+//     the points its bin did catch, and the result is certified against the per-bin counts (every point
+//     of the bins that could hold a nearer point has been looked at).  What cannot be certified is
+//     settled right away by an exact scan of all 360 points, the warp's lanes taking 32 points at a time.
 // Every path is exact with respect to the reference whenever the reference's own selection is not
 // within ~1e-5 degrees of a tie (the parity tests' margin checker uses 2e-4 degrees).
 #pragma once
@@ -65,7 +65,7 @@ struct PolarSmem {
     float2 contour[YCR_C];
     float2 raydir[R];                  // (cos, sin) of i*360/R deg
     float2 anchor[NT];
-    unsigned char cnt[R][NT];          // points per bin (saturating at 255)
+    unsigned char cnt[R][NT];          // points per bin modulo 256 (255 = unknown, see polar_settle_own)
     unsigned short queue[NT / 32][16 * R];  // per warp: (thread << 7) | ray of the pairs the own bin could not settle
     // Settled ray target of (ray i, thread t).  It takes the place of the fourth key of that list: once a
     // ray is settled nothing reads its list again except the .x a neighbouring ray may borrow.
@@ -123,8 +123,9 @@ __device__ __forceinline__ float max_dist2(const PolarSmem<R, NT>& sm, const uin
 }
 
 // One sweep over the contour for the anchor (ax, ay) of this thread.  The per-ray lists stay in
-// shared memory and every point does a uniform read-insert-write on the list of its bin, so the
-// only divergent code is the (rare, two-instruction-deep) step to a neighbouring bin.
+// shared memory and every point does a uniform read-insert-write on the list of its bin; the step
+// to a neighbouring bin is branch-free, so the only divergent code is the walk over several bins
+// (a lane whose anchor sits close to the contour).
 template <int R, int NT>
 __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, float ax, float ay) {
 #pragma unroll 4
@@ -217,7 +218,7 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
                 for (int w = 0; w < u; ++w)
                     if (rb[u0 + w] == rb[u0 + u]) { L[u] = L[w]; c[u] = c[w]; }
                 insert4(L[u].x, L[u].y, L[u].z, L[u].w, pk[u0 + u]);
-                c[u] = min(255u, c[u] + 1u);
+                c[u] += 1u;   // stored modulo 256; polar_settle_own detects a wrapped bin by the total
             }
 #pragma unroll
             for (int u = 0; u < YCR_FWD; ++u) {
@@ -269,11 +270,13 @@ __device__ __forceinline__ int polar_settle_own(PolarSmem<R, NT>& sm, const Pola
     const unsigned lane = threadIdx.x & 31u;
     unsigned short* wq = sm.queue[tid >> 5];
     int nq = 0;
+    unsigned csum = 0;
 YCR_UNROLL(YCR_OWN_UNROLL)
     for (int i = 0; i < R; ++i) {
         bool unsettled = false;
         if (active) {
             const uint4 L = sm.list[i][tid];
+            csum += sm.cnt[i][tid];
             const bool own_gate = (L.x == YCR_EMPTY) || ((L.x >> 9) > pc.q_gate);
             constexpr bool kGateL1 = (180.0 / R - YCR_TOL_DEG) > YCR_GATE_DEG;          // == pc.gate_l1
             constexpr bool kEmpty3 = (3 * 180.0 / R - 3 * YCR_TOL_DEG) > YCR_GATE_DEG;  // == pc.empty3_gate
@@ -309,6 +312,11 @@ YCR_UNROLL(YCR_OWN_UNROLL)
             }
             nq += __popc(ball);
         }
+    }
+    if (active && csum != YCR_C) {
+        // a bin took 256 points or more and its byte count wrapped (the counts must add up to the contour):
+        // mark every bin saturated, which sends this thread's queued pairs to the exact scan
+        for (int i = 0; i < R; ++i) sm.cnt[i][tid] = 255;
     }
     return min(nq, 16 * R);
 }
