@@ -40,7 +40,9 @@
 #define YCR_OWN_UNROLL 2
 #endif
 #define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
+#ifndef YCR_NBR
 #define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
+#endif
 
 struct PolarConst {
     float tan_in;       // tan(hw + TOL): bin membership |crs| <= tan_in * dot

@@ -105,6 +105,25 @@ class v8SegmentationLoss:
         self.lcfg = L.LossCfg(float(box), float(cls))
 
     # -- GT packing: utils/loss.py:834-844 + preprocess utils/loss.py:215-239 ----------------------
+    def _staging(self, n_rows):
+        """(n_rows, 726) view of a pinned host buffer; waits until the copy that last read it has finished."""
+        ev = getattr(self, "_stage_ev", None)
+        if ev is not None:
+            ev.synchronize()
+            self._stage_ev = None
+        buf = getattr(self, "_stage_buf", None)
+        if buf is None or buf.numel() < n_rows * 726:
+            buf = torch.empty(max(n_rows, 64) * 726, dtype=torch.float32).pin_memory()
+            self._stage_buf = buf
+        return buf[:n_rows * 726].view(n_rows, 726)
+
+    @property
+    def last_gt_copy_event(self):
+        """CUDA event recorded right behind the latest host-to-device copy of GT rows (None if there was none
+        or it has been waited for).  A caller that prefetches the next batch on another stream makes that stream
+        wait for it, so the big copy does not overtake the small one this step's kernels depend on."""
+        return getattr(self, "_stage_ev", None)
+
     def pack_targets(self, batch, batch_size, img_hw):
         """-> (packed (B,G,725) device tensor, candidate upper bound).  The rows are assembled on the host
         (they arrive there from the dataloader), copied once, and padded/scaled by a kernel."""
@@ -125,8 +144,15 @@ class v8SegmentationLoss:
                             (bb_h[:, 0] + bb_h[:, 2] / 2) * w, (bb_h[:, 1] + bb_h[:, 3] / 2) * h], 1).contiguous()
         cgrid = L.make_grid(self._shapes, self.stride_list)
         cap = int(L.lib().ycr_candidate_bound_h(C.byref(cgrid), xyxy.data_ptr(), 4, N)) + 64
-        rows = torch.cat([bi.view(-1, 1).to(seg.device), cls.view(-1, 1).to(seg.device), bb.to(seg.device), seg], 1)
-        rows = rows.to(dev, non_blocking=True).contiguous()
+        parts = [bi.view(-1, 1).to(seg.device), cls.view(-1, 1).to(seg.device), bb.to(seg.device), seg]
+        if seg.device.type == "cpu":
+            # assemble the rows in a pinned staging buffer so that the one H2D copy is really asynchronous
+            # (a pageable source makes the host wait for everything queued on the copy engine before it)
+            rows = torch.cat(parts, 1, out=self._staging(N)).to(dev, non_blocking=True)
+            self._stage_ev = torch.cuda.Event()
+            self._stage_ev.record(torch.cuda.current_stream(dev))
+        else:
+            rows = torch.cat(parts, 1).to(dev, non_blocking=True).contiguous()
         out = torch.empty(batch_size, G, 5 + 720, device=dev)
         rc = L.lib().ycr_pack_targets(rows.data_ptr(), rows.stride(0), N, batch_size, G, w, h, out.data_ptr(),
                                       L.stream_ptr(dev))
