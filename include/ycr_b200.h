@@ -199,6 +199,8 @@ typedef struct {
     int max_det, nc, max_nms;
     float max_wh;
     const int* classes; int n_classes; /* optional device list of class ids to keep, utils/ops.py:390 */
+    int compact_rows;   /* 0: image b's rows start at out_rows[b*max_det]; 1: rows of all images back to back
+                         * (image b starts at row sum(out_counts[0..b-1])), so the host can split one tensor */
 } ycr_nms_cfg_t;
 
 size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* cfg);

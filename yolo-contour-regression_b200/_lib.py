@@ -55,7 +55,7 @@ class LossCfg(C.Structure):
 class NmsCfg(C.Structure):
     _fields_ = [("conf_thres", C.c_float), ("iou_thres", C.c_float), ("agnostic", C.c_int),
                 ("multi_label", C.c_int), ("max_det", C.c_int), ("nc", C.c_int), ("max_nms", C.c_int),
-                ("max_wh", C.c_float), ("classes", C.c_void_p), ("n_classes", C.c_int)]
+                ("max_wh", C.c_float), ("classes", C.c_void_p), ("n_classes", C.c_int), ("compact_rows", C.c_int)]
 
 
 EXPORTS = {

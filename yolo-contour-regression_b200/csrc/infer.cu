@@ -411,6 +411,19 @@ __global__ void __launch_bounds__(256) k_nms_gather(const float* __restrict__ pr
     const int b = blockIdx.y;
     const int nc = cfg.nc, W = CH - 4 - nc + 6;
     const int nk = counts[b];
+    if ((int)blockIdx.x * 256 >= nk * W) return;   // block-uniform
+    __shared__ int s_first;
+    if (cfg.compact_rows) {   // first output row of image b = number of rows kept by the images before it
+        if (threadIdx.x < 32) {
+            int s = 0;
+            for (int i = threadIdx.x; i < b; i += 32) s += counts[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) s_first = s;
+        }
+        __syncthreads();
+    }
+    const int64_t first = cfg.compact_rows ? (int64_t)s_first : (int64_t)b * cfg.max_det;
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= nk * W) return;
     const int r = e / W, col = e - r * W;
@@ -421,7 +434,7 @@ __global__ void __launch_bounds__(256) k_nms_gather(const float* __restrict__ pr
     else if (col == 4) v = __int_as_float(k.z);
     else if (col == 5) v = (float)k.y;
     else v = p[(int64_t)(4 + nc + col - 6) * A];
-    out_rows[((int64_t)b * cfg.max_det + r) * W + col] = v;
+    out_rows[(first + r) * W + col] = v;
 }
 
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_ws_layout(nullptr, nullptr, B, A, cfg); }

@@ -56,14 +56,15 @@ def non_max_suppression(
     lib = L.lib()
     nbytes = lib.ycr_nms_workspace_bytes(B, A, CH, C.byref(cfg))
     ws = L.Workspace.get("nms", nbytes, dev)
-    rows = torch.empty(B, max_det, 6 + nm, device=dev, dtype=torch.float32)
+    cfg.compact_rows = 1   # rows of all images back to back: one split instead of B Python slices
+    rows = torch.empty(B * max_det, 6 + nm, device=dev, dtype=torch.float32)
     counts = torch.empty(B, device=dev, dtype=torch.int32)
     rc = lib.ycr_nms(pred.data_ptr(), B, CH, A, C.byref(cfg), rows.data_ptr(), counts.data_ptr(), ws.data_ptr(),
                      ws.numel(), L.stream_ptr(dev))
     L.check(rc, "ycr_nms")
     n = counts.tolist()
     del cls_t
-    return [rows[i, :n[i]] for i in range(B)]
+    return list(torch.split(rows[:sum(n)], n))
 
 
 def resample_segments(segments, n=1000, device=None):
