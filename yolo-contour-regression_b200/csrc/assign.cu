@@ -99,70 +99,111 @@ __device__ __forceinline__ void axis_range(float lo_edge, float hi_edge, float s
     count = max(0, hi - lo + 1);
 }
 
-// One block; GT i of each round of 1024 is handled by thread i, the running candidate / chunk offsets are a
-// block-wide exclusive scan (warp shuffles + one shared array) carried from round to round.
-__global__ void __launch_bounds__(1024) k_gt_setup(GridDev grid, ycr_gt_t gt, AssignWs ws, int chunk) {
-    __shared__ int s_wc[32], s_wk[32];
-    __shared__ int s_carry[2];
+// Candidate rectangles, validity and candidate count of every GT (one thread per GT, any number of blocks).
+__global__ void __launch_bounds__(128) k_gt_rects(GridDev grid, ycr_gt_t gt, AssignWs ws) {
+    const int BG = gt.B * gt.G;
+    const int bg = blockIdx.x * 128 + threadIdx.x;
+    if (bg >= BG) return;
+    const float* bx = gt.boxes + (int64_t)bg * gt.boxes_stride;
+    const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+    const bool valid = gt.mask_gt ? (gt.mask_gt[(int64_t)bg * gt.mask_stride] != 0.f) : ((x1 + y1 + x2 + y2) > 0.f);
+    int n = 0;
+    for (int l = 0; l < grid.n_levels; ++l) {
+        int fx = 0, cx = 0, fy = 0, cy = 0;
+        if (valid) {
+            axis_range(x1, x2, grid.stride[l], grid.w[l], fx, cx);
+            axis_range(y1, y2, grid.stride[l], grid.h[l], fy, cy);
+            if (cx == 0 || cy == 0) cx = cy = 0;
+        }
+        ws.rect[bg * YCR_MAX_LEVELS + l] = make_int4(fx, fy, cx, cy);
+        n += cx * cy;
+    }
+    ws.valid[bg] = valid ? 1 : 0;
+    ws.ncand[bg] = n;
+}
+
+// One block; GT i of each round of 1024 is handled by thread i, the running candidate / chunk / partial-chunk
+// offsets are block-wide exclusive scans (warp shuffles + shared arrays) carried from round to round.  The
+// last phase lays out the order in which K1 draws the chunks: the full chunks of all GTs first, then the
+// partial chunk of every GT that has one - the cheapest work last keeps the tail of the persistent kernel short.
+__global__ void __launch_bounds__(1024) k_gt_setup(ycr_gt_t gt, AssignWs ws, int chunk) {
+    __shared__ int s_wc[32], s_wk[32], s_wp[32];
+    __shared__ int s_carry[3];
+    __shared__ int s_n[1024], s_first[1024], s_po[1024];
     const int BG = gt.B * gt.G;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    if (t == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    if (t == 0) { s_carry[0] = 0; s_carry[1] = 0; s_carry[2] = 0; }
     __syncthreads();
     for (int base = 0; base < BG; base += 1024) {
         const int bg = base + t;
-        int n = 0, nk = 0;
+        int n = 0, nk = 0, np = 0;
         if (bg < BG) {
-            const float* bx = gt.boxes + (int64_t)bg * gt.boxes_stride;
-            const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
-            const bool valid = gt.mask_gt ? (gt.mask_gt[(int64_t)bg * gt.mask_stride] != 0.f) : ((x1 + y1 + x2 + y2) > 0.f);
-            for (int l = 0; l < grid.n_levels; ++l) {
-                int fx = 0, cx = 0, fy = 0, cy = 0;
-                if (valid) {
-                    axis_range(x1, x2, grid.stride[l], grid.w[l], fx, cx);
-                    axis_range(y1, y2, grid.stride[l], grid.h[l], fy, cy);
-                    if (cx == 0 || cy == 0) cx = cy = 0;
-                }
-                ws.rect[bg * YCR_MAX_LEVELS + l] = make_int4(fx, fy, cx, cy);
-                n += cx * cy;
-            }
-            ws.valid[bg] = valid ? 1 : 0;
-            ws.ncand[bg] = n;
+            n = ws.ncand[bg];   // k_gt_rects
             nk = (n + chunk - 1) / chunk;
+            np = (n % chunk) ? 1 : 0;
         }
         // inclusive scans inside the warp, then across the 32 warp totals
-        int ic = n, ik = nk;
+        int ic = n, ik = nk, ip = np;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int vc = __shfl_up_sync(0xffffffffu, ic, o), vk = __shfl_up_sync(0xffffffffu, ik, o);
-            if (lane >= o) { ic += vc; ik += vk; }
+            const int vp = __shfl_up_sync(0xffffffffu, ip, o);
+            if (lane >= o) { ic += vc; ik += vk; ip += vp; }
         }
-        if (lane == 31) { s_wc[wid] = ic; s_wk[wid] = ik; }
+        if (lane == 31) { s_wc[wid] = ic; s_wk[wid] = ik; s_wp[wid] = ip; }
         __syncthreads();
         if (wid == 0) {
-            int wc = s_wc[lane], wk = s_wk[lane];
+            int wc = s_wc[lane], wk = s_wk[lane], wp = s_wp[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int vc = __shfl_up_sync(0xffffffffu, wc, o), vk = __shfl_up_sync(0xffffffffu, wk, o);
-                if (lane >= o) { wc += vc; wk += vk; }
+                const int vp = __shfl_up_sync(0xffffffffu, wp, o);
+                if (lane >= o) { wc += vc; wk += vk; wp += vp; }
             }
             s_wc[lane] = wc;
             s_wk[lane] = wk;
+            s_wp[lane] = wp;
         }
         __syncthreads();
         const int run_c = s_carry[0] + (wid ? s_wc[wid - 1] : 0) + ic - n;
         const int run_k = s_carry[1] + (wid ? s_wk[wid - 1] : 0) + ik - nk;
+        const int run_p = s_carry[2] + (wid ? s_wp[wid - 1] : 0) + ip - np;
         if (bg < BG) {
             ws.cand_off[bg] = run_c;
             ws.chunk_off[bg] = run_k;
-            for (int k = 0; k < nk; ++k)
-                if (run_k + k < ws.chunks_cap) ws.chunk_bg[run_k + k] = bg;
+            ws.part_off[bg] = run_p;
+        }
+        s_n[t] = nk - np;                 // full chunks of this GT
+        s_first[t] = run_k;
+        s_po[t] = run_k - run_p;          // full chunks of all GTs before it = its first hand-out slot
+        __syncthreads();
+        if (t == 1023) { s_carry[0] = run_c + n; s_carry[1] = run_k + nk; s_carry[2] = run_p + np; }
+        // hand-out entries of the full chunks of this round's GTs: one thread per entry, the GT found by
+        // binary search in the (non-decreasing) first slots - the owner of slot u is the last GT whose first
+        // slot is <= u
+        {
+            const int nround = min(1024, BG - base);
+            const int u_begin = s_po[0], u_end = s_po[nround - 1] + s_n[nround - 1];
+            for (int u = u_begin + t; u < u_end; u += 1024) {
+                int lo = 0, hi = nround - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_po[mid] <= u) lo = mid; else hi = mid - 1;
+                }
+                if (u < ws.chunks_cap) { ws.chunk_bg[u] = base + lo; ws.chunk_work[u] = s_first[lo] + (u - s_po[lo]); }
+            }
         }
         __syncthreads();
-        if (t == 1023) { s_carry[0] = run_c + n; s_carry[1] = run_k + nk; }
-        __syncthreads();
+    }
+    const int M = s_carry[0], T = s_carry[1], P = s_carry[2];
+    for (int bg = t; bg < BG; bg += 1024) {   // the partial chunks go behind all full ones
+        const int n = ws.ncand[bg];
+        if (n % chunk) {
+            const int u = T - P + ws.part_off[bg];
+            if (u < ws.chunks_cap) { ws.chunk_bg[u] = bg; ws.chunk_work[u] = ws.chunk_off[bg] + n / chunk; }
+        }
     }
     if (t == 0) {
-        const int M = s_carry[0], T = s_carry[1];
         ws.cand_off[BG] = M;
         ws.chunk_off[BG] = T;
         ws.totals[0] = M;
@@ -215,12 +256,14 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
     int n_work = T, n_bg = -1, n_desc = 0;
     float n_contour[CW];
     auto fetch_next = [&](int drawn) {          // warp 0, all lanes; `drawn` valid in lane 0
-        n_work = __shfl_sync(0xffffffffu, drawn, 0);
+        const int unit = __shfl_sync(0xffffffffu, drawn, 0);
+        n_work = T;
         n_bg = -1;
-        if (n_work < T) {
-            int bgl = 0;
-            if (tid == 0) bgl = ws.chunk_bg[n_work];
+        if (unit < T) {
+            int bgl = 0, wl = 0;
+            if (tid == 0) { bgl = ws.chunk_bg[unit]; wl = ws.chunk_work[unit]; }
             n_bg = __shfl_sync(0xffffffffu, bgl, 0);
+            n_work = __shfl_sync(0xffffffffu, wl, 0);
             const float* cp = a.gt.coor + (int64_t)n_bg * a.gt.coor_stride;
 #pragma unroll
             for (int k = 0; k < CW; ++k)
@@ -824,6 +867,8 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
     w.chunk_off = al.take<int>(BG + 1);
     const size_t chunks_cap = (size_t)cand_cap / K1_NT + (size_t)BG + 1;  // every GT adds at most one partial chunk
     w.chunk_bg = al.take<int>(chunks_cap);
+    w.chunk_work = al.take<int>(chunks_cap);
+    w.part_off = al.take<int>(BG + 1);
     w.chunks_cap = (int)chunks_cap;
     w.valid = al.take<uint8_t>(BG + 1);
     w.totals = al.take<int>(4);
@@ -884,7 +929,11 @@ int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cu
         YCR_CUDA_CHECK(cudaMemsetAsync(ws.totals, 0, 4 * sizeof(int), st));
     }
     if (BG > 0) {
-        { YcrProfScope ps(YCR_T_SETUP, st); k_gt_setup<<<1, 1024, 0, st>>>(a.grid, a.gt, ws, K1_NT); }
+        {
+            YcrProfScope ps(YCR_T_SETUP, st);
+            k_gt_rects<<<(BG + 127) / 128, 128, 0, st>>>(a.grid, a.gt, ws);
+            k_gt_setup<<<1, 1024, 0, st>>>(a.gt, ws, K1_NT);
+        }
         YCR_LAUNCH_CHECK();
         int rc = (a.cfg.rays == 36) ? launch_k1<36>(a, ws, st) : launch_k1<72>(a, ws, st);
         if (rc) return rc;

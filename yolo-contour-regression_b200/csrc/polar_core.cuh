@@ -512,7 +512,9 @@ __device__ __forceinline__ int polar_settle_queue_shared(PolarSmem<R, NT>& sm, c
         int n = nq;
         if (turn == 1) {
             // every lane polls (uniform control flow; the value changes once, from -1 to the length)
-            while ((n = ctl[qw]) < 0) __nanosleep(100);
+            // (back-off: an idle warp of a half-empty chunk waits here for the other warp's whole sweep, and
+            // the kernel is issue-bound)
+            for (unsigned ns = 64; (n = ctl[qw]) < 0; ns = min(ns * 2, 2048u)) __nanosleep(ns);
             __threadfence_block();
             __syncwarp();
         }
@@ -531,7 +533,7 @@ __device__ __forceinline__ int polar_settle_queue_shared(PolarSmem<R, NT>& sm, c
             __syncwarp();
         }
     }
-    while (ctl[4 + w] < nq) __nanosleep(100);
+    for (unsigned ns = 32; ctl[4 + w] < nq; ns = min(ns * 2, 1024u)) __nanosleep(ns);
     __threadfence_block();
     __syncwarp();
     return nscan;

@@ -10,7 +10,9 @@ struct AssignWs {
     int* ncand;        // [BG]
     int* cand_off;     // [BG+1]
     int* chunk_off;    // [BG+1]
-    int* chunk_bg;     // [chunks_cap] GT of every chunk (saves the per-chunk binary search in K1)
+    int* chunk_bg;     // [chunks_cap] hand-out order of K1: GT of the u-th chunk drawn ...
+    int* chunk_work;   // [chunks_cap] ... and its chunk index (full chunks first, the cheaper partial ones last)
+    int* part_off;     // [BG+1] number of GTs before this one that have a partial chunk
     int chunks_cap;
     uint8_t* valid;    // [BG]
     int* totals;       // [4] = {M, T, K1 work counter, -}
