@@ -385,9 +385,9 @@ def run_ours(args):
         "loss_stream_hbm_frac": (stream_bytes / (kern["loss_stream"] * 1e-3) / 1e9 / peak) if "loss_stream" in kern else None,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": in_bytes + gt_rows_bytes,
                 "d2h_bytes_per_step": 4, "steps": e_steps},
-        # per step: k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image, k_positive_gather,
+        # per step: k_gt_rects, k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image, k_positive_gather,
         # k_loss_stream_v4, k_loss_finalize, k_scale (torch's two gradient fills are not counted)
-        "gpu_launches": 8 * args.steps,
+        "gpu_launches": 9 * args.steps,
         "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
                   "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",
                   "ms_per_step": ms_inf / i_steps, "kernels_ms": ikern,
@@ -407,7 +407,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
