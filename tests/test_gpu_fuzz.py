@@ -1,0 +1,56 @@
+"""GPU: randomised small configurations (image size, batch, GT count incl. ragged / empty images, class
+count, 36 and 72 rays) against the oracle - every path of the candidate kernel (own-bin settlement, queued
+pairs, exact scans, half-empty chunks, queue sharing between the two warps of a block, chunk hand-out order)
+gets inputs the fixed golden cases do not contain.  Only tie-free draws (the oracle's margin checker: every
+assignment decision certain, no positive with an ambiguous ray target) are compared."""
+import pytest
+import torch
+
+from oracle import polar_oracle as po
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+CASES = [
+    # (batch, gts, imgsz, rays, nc, ragged, seed)
+    (1, 1, 64, 36, 1, False, 101),
+    (3, 2, 96, 36, 3, True, 102),
+    (2, 7, 160, 36, 80, False, 103),
+    (5, 3, 128, 36, 10, True, 104),
+    (2, 12, 224, 36, 2, True, 105),
+    (1, 4, 320, 36, 20, False, 106),
+    (4, 1, 192, 36, 5, False, 107),
+    (2, 3, 160, 72, 4, True, 108),
+    (1, 6, 256, 72, 10, False, 109),
+    (3, 5, 288, 36, 7, True, 110),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"b{c[0]}g{c[1]}s{c[2]}r{c[3]}" for c in CASES])
+def test_random_config_matches_oracle(case):
+    from ycr_b200 import synth
+    from ycr_b200.loss import v8SegmentationLoss
+    B, G, S, R, nc, ragged, seed0 = case
+    dev = torch.device("cuda:0")
+    cfg = synth.PathConfig("fz", B, G, S, rays=R, nc=nc)
+    crit = v8SegmentationLoss(nc=nc, nm=R, strides=cfg.strides, device=dev)
+    compared = tried = 0
+    for seed in range(seed0 * 10, seed0 * 10 + 4):
+        batch = synth.make_gts(cfg, seed, ragged=ragged)
+        feats = synth.make_feats_near_gt(cfg, seed, batch) if seed % 2 else synth.make_feats(cfg, seed)
+        ref = po.seg_loss(feats, batch, cfg.strides, nc, R)
+        fg = [f.to(dev).requires_grad_(True) for f in feats]
+        total, items = crit((fg, 5, 2), batch)
+        total.backward()
+        assert bool(torch.isfinite(total))
+        tried += 1
+        if not bool(ref["assign"]["certain"].all()) or bool(ref["assign"]["gt_dist_ambiguous"].any()):
+            continue   # a near-tie among the four nearest points of some positive's ray: the loss is not pinned
+        compared += 1
+        assert rel_err(items.cpu(), ref["loss_items"]) < TOL, (case, seed)
+        for f, r in zip(fg, ref["grads"]):
+            assert float((f.grad.cpu() - r).abs().max()) <= TOL * max(float(r.abs().max()), 1e-30), (case, seed)
+        if compared == 2:
+            break
+    assert compared >= 1 or tried >= 4

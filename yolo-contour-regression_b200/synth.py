@@ -107,7 +107,7 @@ def make_feats(cfg: PathConfig, seed: int, batch: int | None = None, hot_cells: 
         mean = rng.uniform(-6.0, -3.0, size=(B, cfg.nc, 1, 1)).astype(np.float32)
         logit = rng.standard_normal((B, cfg.nc, h, w), dtype=np.float32) + mean
         n_hot = max(1, hot_cells // (2 ** li))
-        for b in range(B):
+        for b in range(B if (h > 2 and w > 2) else 0):   # (grids of 2x2 cells have no interior cell)
             ys = rng.integers(1, h - 1, size=n_hot)
             xs = rng.integers(1, w - 1, size=n_hot)
             cs = rng.integers(0, cfg.nc, size=n_hot)
