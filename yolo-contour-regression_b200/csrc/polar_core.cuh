@@ -128,8 +128,16 @@ __device__ __forceinline__ float max_dist2(const PolarSmem<R, NT>& sm, const uin
 // shared memory and every point does a uniform read-insert-write on the list of its bin; the step
 // to a neighbouring bin is branch-free, so the only divergent code is the walk over several bins
 // (a lane whose anchor sits close to the contour).
+// Bins narrower than the 3 degree gate (R > 60, e.g. 72 rays: +-2.5 deg) would rarely hold four points and
+// never certify the gate.  There every point is inserted into the lists of BOTH rays that bracket it, so the
+// list of ray i holds the nearest of all points within +-360/R deg (minus TOL) of it - the same situation as
+// 36 rays with their +-5 deg bins; tracking, counts and windows keep using the disjoint half-spacing bins.
+template <int R>
+struct PolarDual { static constexpr bool value = (180.0 / R + YCR_TOL_DEG) <= YCR_GATE_DEG; };
+
 template <int R, int NT>
 __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarConst& pc, int tid, float ax, float ay) {
+    constexpr bool kDual = PolarDual<R>::value;
 #pragma unroll 4
     for (int i = 0; i < R; ++i) {
         sm.list[i][tid] = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
@@ -161,6 +169,8 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
         // the start of every group, so at most PPS rotations (a few 1e-6 deg) ever accumulate.
         int rb[YCR_GROUP];
         uint32_t pk[YCR_GROUP];
+        int rb2[YCR_GROUP];        // kDual: the other ray that brackets the point, and the key against it
+        uint32_t pk2[YCR_GROUP];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             int ry = ray[s];
@@ -198,6 +208,15 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
                 rb[u] = ry;
                 const float key = fabsf(crs) * inv[u];
                 pk[u] = (__float_as_uint(fmaf(key, ks, 8388608.f)) << 9) | (uint32_t)(s * SEG + j0 + k);
+                if constexpr (kDual) {
+                    const bool up2 = crs >= 0.f;
+                    const float s2 = up2 ? sstep : -sstep;
+                    const float crsn = fmaf(crs, cstep, -dot * s2);   // cross against the neighbouring ray
+                    int r2 = ry + (up2 ? 1 : -1);
+                    r2 = (r2 < 0) ? R - 1 : ((r2 >= R) ? 0 : r2);
+                    rb2[u] = r2;
+                    pk2[u] = (__float_as_uint(fmaf(fabsf(crsn) * inv[u], ks, 8388608.f)) << 9) | (uint32_t)(s * SEG + j0 + k);
+                }
             }
             ray[s] = ry;
         }
@@ -226,6 +245,16 @@ __device__ __forceinline__ void polar_sweep(PolarSmem<R, NT>& sm, const PolarCon
             for (int u = 0; u < YCR_FWD; ++u) {
                 sm.list[rb[u0 + u]][tid] = L[u];
                 sm.cnt[rb[u0 + u]][tid] = (unsigned char)c[u];
+            }
+        }
+        if constexpr (kDual) {
+            // second insertion (lists only - the counts stay those of the disjoint bins), one point after
+            // the other through shared memory
+#pragma unroll
+            for (int u = 0; u < YCR_GROUP; ++u) {
+                uint4 L = sm.list[rb2[u]][tid];
+                insert4(L.x, L.y, L.z, L.w, pk2[u]);
+                sm.list[rb2[u]][tid] = L;
             }
         }
     }
@@ -280,7 +309,8 @@ YCR_UNROLL(YCR_OWN_UNROLL)
             const uint4 L = sm.list[i][tid];
             csum += sm.cnt[i][tid];
             const bool own_gate = (L.x == YCR_EMPTY) || ((L.x >> 9) > pc.q_gate);
-            constexpr bool kGateL1 = (180.0 / R - YCR_TOL_DEG) > YCR_GATE_DEG;          // == pc.gate_l1
+            constexpr double kHwEff = PolarDual<R>::value ? 360.0 / R : 180.0 / R;     // reach of a list
+            constexpr bool kGateL1 = (kHwEff - YCR_TOL_DEG) > YCR_GATE_DEG;             // == pc.gate_l1
             constexpr bool kEmpty3 = (3 * 180.0 / R - 3 * YCR_TOL_DEG) > YCR_GATE_DEG;  // == pc.empty3_gate
             bool gate = own_gate && kGateL1;
             if (!kGateL1 && kEmpty3 && L.x == YCR_EMPTY) {
@@ -556,12 +586,14 @@ static inline PolarConst make_polar_const(int R) {
     pc.tan_in = (float)tan(ycr_deg2rad(hw + T));
     pc.cos_step = (float)cos(ycr_deg2rad(2 * hw));
     pc.sin_step = (float)sin(ycr_deg2rad(2 * hw));
-    const double scale = 8388607.0 / sin(ycr_deg2rad(hw + 2 * T));
+    // reach of a list: the bin, or - bins narrower than the gate (PolarDual) - the two bins around the ray
+    const double hw_eff = (hw + T <= YCR_GATE_DEG) ? 2 * hw : hw;
+    const double scale = 8388607.0 / sin(ycr_deg2rad(hw_eff + 2 * T));
     pc.key_scale = (float)scale;
-    pc.q_res = (uint32_t)(sin(ycr_deg2rad(hw - 2 * T)) * scale);
+    pc.q_res = (uint32_t)(sin(ycr_deg2rad(hw_eff - 2 * T)) * scale);
     pc.q_gate = (uint32_t)(sin(ycr_deg2rad(YCR_GATE_DEG)) * scale);
-    if (YCR_GATE_DEG >= hw + T) pc.q_gate = 0x7FFFFFu;  // every in-bin key is below the gate
-    pc.gate_l1 = (hw - T > YCR_GATE_DEG) ? 1 : 0;
+    if (YCR_GATE_DEG >= hw_eff + T) pc.q_gate = 0x7FFFFFu;  // every listed key is below the gate
+    pc.gate_l1 = (hw_eff - T > YCR_GATE_DEG) ? 1 : 0;
     pc.empty3_gate = (3 * hw - 3 * T > YCR_GATE_DEG) ? 1 : 0;
     pc.nwin = R / 2 + 1;
     for (int m = 0; m < YCR_MAXWIN; ++m) {
