@@ -207,7 +207,8 @@ size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* 
 
 /* Replaces ops.non_max_suppression, polar variant (utils/ops.py:285-424) including the
  * torchvision.ops.nms step (utils/ops.py:407).  prediction (B, 4+nc+nm, A).
- *   out_rows   (B, max_det, 6+nm): kept rows in descending-score order
+ *   out_rows   B*max_det rows of 6+nm floats: kept rows in descending-score order, image b's rows at
+ *              row b*max_det (cfg->compact_rows == 0) or directly behind image b-1's (compact_rows == 1)
  *   out_counts (B) device int: rows kept per image */
 int ycr_nms(const float* prediction, int B, int channels, int A, const ycr_nms_cfg_t* cfg, float* out_rows,
             int* out_counts, void* workspace, size_t workspace_bytes, void* stream);

@@ -149,3 +149,42 @@ def test_segment_head_forward_contract():
     assert allpred.shape == (2, 4 + 10 + 108, 525) and one == 1 and allpred2 is allpred
     ref = po.decode([f.cpu() for f in feats2], (8, 16, 32), 10, 36)
     assert bool(((allpred.cpu() - ref).abs() <= 1e-5 * ref.abs() + 1e-5).all())
+
+
+def test_nms_padded_and_compact_row_layouts_agree():
+    """The C ABI offers both output layouts (ycr_nms_cfg_t.compact_rows); the Python mirror uses the compact
+    one.  Same kept rows, same counts, including images that keep nothing."""
+    import ctypes as C
+    from ycr_b200 import _lib as L
+    from ycr_b200.ops import non_max_suppression
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    B, nc, R, A = 5, 3, 36, 600
+    CH = 4 + nc + 3 * R
+    pred = torch.zeros(B, CH, A)
+    xy = torch.rand(B, 2, A, generator=g) * 500
+    wh = torch.rand(B, 2, A, generator=g) * 80 + 5
+    pred[:, 0:2] = xy
+    pred[:, 2:4] = xy + wh
+    pred[:, 4:4 + nc] = torch.rand(B, nc, A, generator=g) * 0.6
+    pred[2, 4:4 + nc] = 0.01                                   # image 2 keeps nothing
+    pred[:, 4 + nc:] = torch.rand(B, 3 * R, A, generator=g)
+    pred = pred.to(dev)
+    ref = non_max_suppression(pred, 0.25, 0.5, nc=nc, max_det=50)
+    assert ref[2].shape[0] == 0 and sum(r.shape[0] for r in ref) > 0
+    cfg = L.NmsCfg()
+    cfg.conf_thres, cfg.iou_thres, cfg.agnostic, cfg.multi_label = 0.25, 0.5, 0, 0
+    cfg.max_det, cfg.nc, cfg.max_nms, cfg.max_wh, cfg.classes, cfg.n_classes = 50, nc, 30000, 7680.0, None, 0
+    cfg.compact_rows = 0
+    lib = L.lib()
+    ws = torch.empty(lib.ycr_nms_workspace_bytes(B, A, CH, C.byref(cfg)), dtype=torch.uint8, device=dev)
+    rows = torch.full((B, 50, 6 + 3 * R), -1.0, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    rc = lib.ycr_nms(pred.data_ptr(), B, CH, A, C.byref(cfg), rows.data_ptr(), cnt.data_ptr(), ws.data_ptr(),
+                     ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "ycr_nms")
+    n = cnt.tolist()
+    assert n == [r.shape[0] for r in ref]
+    for b in range(B):
+        assert torch.equal(rows[b, :n[b]], ref[b])
+        assert bool((rows[b, n[b]:] == -1.0).all())            # nothing written beyond the kept rows
