@@ -103,13 +103,18 @@ def _random_pred(rng, B, A, nc, nm, n_hot, dup=False):
     (8400, 1500, dict(conf_thres=0.25, iou_thres=0.5, classes=[0, 2], multi_label=True)),
     (8400, 3000, dict(conf_thres=0.25, iou_thres=0.5, max_nms=1000)),
     (8400, 1500, dict(conf_thres=0.25, iou_thres=0.5, agnostic=True)),
+    # the validator's regime: conf 0.001 with multi-label lets ~67 k (anchor, class) pairs per image through,
+    # more than twice max_nms - the kernel selects the best max_nms before sorting
+    (8400, 1501, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_det=300, _batch=1)),
+    (8400, 1502, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True, max_nms=5000, max_det=100, _batch=1)),
 ])
 def test_nms_random_vs_oracle(A, n_hot, kw):
     from ycr_b200.ops import non_max_suppression
     dev = _dev()
     rng = np.random.default_rng(A + n_hot)
     nc, nm = 8, 12
-    pred = _random_pred(rng, 3, A, nc, nm, n_hot, dup=True)
+    kw = dict(kw)
+    pred = _random_pred(rng, kw.pop("_batch", 3), A, nc, nm, n_hot, dup=True)
     ref, margin = po.nms(pred, nc=nc, **kw)
     assert margin > 1e-6
     dets = non_max_suppression(pred.to(dev), nc=nc, **kw)

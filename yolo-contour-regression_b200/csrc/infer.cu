@@ -178,7 +178,8 @@ struct NmsWs {
     int* count;                // [B] candidates written (may exceed cap)
     float4* boxes;             // [B][nsel_cap] class-offset boxes in sorted order
     int4* kept;                // [B][NMS_MAX_KEEP] (anchor, class, score bits, -) of the kept rows
-    int cap, cap2, nsel_cap;
+    unsigned long long* keys2;  // [B][presel_cap2] the preselected candidates (only when cap > NMS_PRESEL_MIN)
+    int cap, cap2, nsel_cap, presel_cap2;
 };
 
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -195,6 +196,12 @@ static size_t nms_ws_layout(NmsWs* ws, void* base, int B, int A, const ycr_nms_c
     w.count = al.take<int>(B + 1);
     w.boxes = al.take<float4>((size_t)B * w.nsel_cap + 1);
     w.kept = al.take<int4>((size_t)B * 1024);
+    w.presel_cap2 = 0;
+    w.keys2 = nullptr;
+    if (w.cap > 32768 && w.cap > w.nsel_cap) {
+        w.presel_cap2 = next_pow2(2 * w.nsel_cap);
+        w.keys2 = al.take<unsigned long long>((size_t)B * w.presel_cap2);
+    }
     if (ws) *ws = w;
     return align_up(al.off, 256);
 }
@@ -261,27 +268,98 @@ __device__ void bitonic_sort(unsigned long long* d, int npow2) {
 }
 
 #define NMS_SORT_SMEM 4096
+#define NMS_PRESEL_MIN 32768   // above this many candidates the top max_nms are selected before sorting
+
+// Radix selection (block-wide): among the first n keys of `keys`, find the 32-bit prefix T (the complemented
+// score bits, i.e. the high word of a key) such that fewer than `want` keys have a smaller prefix and at
+// least `want` have a prefix <= T; returns T and the number of keys with prefix <= T.  Three histogram passes
+// (12 + 12 + 8 bits) in shared memory.
+__device__ unsigned nms_radix_threshold(const unsigned long long* keys, int n, int want, int* s_hist, int* s_out,
+                                        int& n_le) {
+    unsigned prefix = 0;        // bits decided so far (left-aligned in 32 bits)
+    int before = 0;             // keys whose decided bits are smaller
+    const int widths[3] = {12, 12, 8};
+    int decided = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int w = widths[pass], nb = 1 << w, shift = 32 - decided - w;
+        for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned hi = (unsigned)(keys[i] >> 32);
+            const bool in = (decided == 0) || ((hi >> (32 - decided)) == (prefix >> (32 - decided)));
+            if (in) atomicAdd(&s_hist[(hi >> shift) & (nb - 1)], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int cum = before, bsel = nb - 1;
+            for (int k = 0; k < nb; ++k) {
+                if (cum + s_hist[k] >= want) { bsel = k; break; }
+                cum += s_hist[k];
+            }
+            s_out[0] = bsel;
+            s_out[1] = cum;                      // keys strictly before the selected bin
+            s_out[2] = cum + s_hist[bsel];       // keys up to and including it
+        }
+        __syncthreads();
+        prefix |= (unsigned)s_out[0] << shift;
+        before = s_out[1];
+        n_le = s_out[2];
+        decided += w;
+        __syncthreads();
+    }
+    return prefix;
+}
 
 // per image: sort candidates by (score desc, input order asc) = stable descending sort
 // (torchvision nms_kernel: scores.sort(0, descending=True)); cut to max_nms (utils/ops.py:401-402);
 // emit class-offset boxes `x[:, :4] + cls * max_wh` in fp32 (utils/ops.py:405-406).
+// When far more candidates pass the filter than max_nms keeps (the validator's conf 0.001 with multi-label:
+// ~10^5..10^6 per image), the max_nms best are selected first (radix selection on the score bits, all keys
+// tied with the threshold included) and only those are sorted.
 __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
     __shared__ unsigned long long s_keys[NMS_SORT_SMEM];
+    __shared__ int s_out[4];
     const int b = blockIdx.x;
     unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
     const int n = min(ws.count[b], ws.cap);
     if (n == 0) return;
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    if (np2 <= NMS_SORT_SMEM) {
-        for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = (i < n) ? keys[i] : 0xFFFFFFFFFFFFFFFFull;
-        __syncthreads();
-        bitonic_sort(s_keys, np2);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = s_keys[i];
-    } else {
-        for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0xFFFFFFFFFFFFFFFFull;
-        __syncthreads();
-        bitonic_sort(keys, np2);
+    bool sorted = false;
+    if (ws.keys2 && n > NMS_PRESEL_MIN && n > ws.nsel_cap) {
+        int n_le = 0;
+        const unsigned T = nms_radix_threshold(keys, n, ws.nsel_cap, reinterpret_cast<int*>(s_keys), s_out, n_le);
+        if (n_le <= ws.presel_cap2) {   // (block-uniform) otherwise too many ties: sort everything
+            unsigned long long* sel = ws.keys2 + (int64_t)b * ws.presel_cap2;
+            if (threadIdx.x == 0) s_out[3] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned long long k = keys[i];
+                if ((unsigned)(k >> 32) <= T) sel[atomicAdd(&s_out[3], 1)] = k;
+            }
+            __syncthreads();
+            const int m = s_out[3];     // == n_le
+            int mp2 = 1;
+            while (mp2 < m) mp2 <<= 1;
+            for (int i = m + threadIdx.x; i < mp2; i += blockDim.x) sel[i] = 0xFFFFFFFFFFFFFFFFull;
+            __syncthreads();
+            bitonic_sort(sel, mp2);
+            for (int i = threadIdx.x; i < ws.nsel_cap; i += blockDim.x) keys[i] = sel[i];
+            __syncthreads();
+            sorted = true;
+        }
+    }
+    if (!sorted) {
+        int np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        if (np2 <= NMS_SORT_SMEM) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = (i < n) ? keys[i] : 0xFFFFFFFFFFFFFFFFull;
+            __syncthreads();
+            bitonic_sort(s_keys, np2);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = s_keys[i];
+        } else {
+            for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0xFFFFFFFFFFFFFFFFull;
+            __syncthreads();
+            bitonic_sort(keys, np2);
+        }
     }
     __syncthreads();
     const int nsel = min(n, ws.nsel_cap);
