@@ -394,3 +394,20 @@ def test_clustered_contour_bin_count_wraps():
     ref_ov = po.polar_iou(prays[0, sub], rt["t"])
     assert int(clean.sum()) > 30
     assert rel_err(ov[sub][clean], ref_ov[clean]) < TOL
+
+
+def test_assigner_grid_recovered_from_anchors():
+    """Without `ss`/`imgsz` (and without the `grid` extension) the level shapes come from the anchors and the
+    stride column themselves; same result as with the explicit grid."""
+    from ycr_b200.tal import TaskAlignedAssigner
+    dev = _dev()
+    g = load_golden("train_s320_ragged")
+    cfg, feats, batch = train_inputs(g)
+    cpu, gpu, shapes = _assigner_inputs(cfg, feats, batch, dev)
+    asg = TaskAlignedAssigner(topk=10, num_classes=cfg.nc, alpha=0.5, beta=4.0)
+    a = asg(gpu["scores"], gpu["rays"], gpu["anc"], gpu["gl"], gpu["gb"], gpu["mask_gt"], gpu["gc"], gpu["st"],
+            gpu["ss"], 0, None, grid=(shapes, list(cfg.strides)))
+    b = asg(gpu["scores"], gpu["rays"], gpu["anc"], gpu["gl"], gpu["gb"], gpu["mask_gt"], gpu["gc"], gpu["st"],
+            None, 0, None)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

@@ -76,6 +76,30 @@ class TaskAlignedAssigner(nn.Module):
         self.debug_metrics = False  # also return dense overlaps / align_metric (tests)
         self._grid_cache = {}
 
+    def _grid_from_anchors(self, anc_points, stride_tensor, A):
+        """Level shapes recovered from the anchors themselves (when the caller passes neither `ss`/`imgsz` nor
+        `grid`): a level is a run of equal strides, its width the length of the first run of increasing x."""
+        st = stride_tensor.detach().reshape(-1).float().cpu()
+        xs = anc_points.detach()[:, 0].float().cpu()
+        if st.numel() != A or xs.numel() != A:
+            raise ValueError("anc_points / stride_tensor do not describe the anchors of pd_scores")
+        cuts = [0] + (torch.nonzero(st[1:] != st[:-1]).flatten() + 1).tolist() + [A]
+        key = (A, tuple(cuts))
+        g = self._grid_cache.get(key)
+        if g is None:
+            shapes, strides = [], []
+            for lo, hi in zip(cuts[:-1], cuts[1:]):
+                x = xs[lo:hi]
+                wrap = torch.nonzero(x[1:] <= x[:-1]).flatten()
+                w = int(wrap[0]) + 1 if wrap.numel() else hi - lo
+                if (hi - lo) % w:
+                    raise ValueError("anchor layout is not the make_anchors_polar grid")
+                shapes.append(((hi - lo) // w, w))
+                strides.append(float(st[lo]))
+            g = (shapes, strides)
+            self._grid_cache[key] = g
+        return g
+
     def _grid(self, ss, imgsz, A):
         key = (A, tuple(int(s.shape[0]) for s in ss))
         g = self._grid_cache.get(key)
@@ -113,7 +137,12 @@ class TaskAlignedAssigner(nn.Module):
                     torch.zeros_like(pd_scores), torch.zeros(B, 0, A, dtype=torch.bool, device=dev),
                     torch.zeros(B, A, dtype=torch.int64, device=dev), torch.zeros(0, R, device=dev),
                     torch.zeros(0, device=dev), torch.zeros(B, A, dtype=torch.bool, device=dev))
-        shapes, strides = grid if grid is not None else self._grid(ss, imgsz, A)
+        if grid is not None:
+            shapes, strides = grid
+        elif ss is not None and imgsz is not None:
+            shapes, strides = self._grid(ss, imgsz, A)
+        else:
+            shapes, strides = self._grid_from_anchors(anc_points, stride_tensor, A)
         cgrid = L.make_grid(shapes, strides)
         scores = pd_scores.float().contiguous()
         rays = pd_bboxes.float().contiguous()
