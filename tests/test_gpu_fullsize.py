@@ -191,3 +191,24 @@ def test_c3_decode_and_nms_properties():
     pred2[0, 4 + nc:] = d[:, 6:].T
     again = non_max_suppression(pred2, 0.25, 0.7, nc=nc, max_det=300)[0]
     assert again.shape[0] == d.shape[0] and torch.equal(again[:, :6], d[:, :6])
+
+
+def test_c2_loss_bit_identical_run_to_run():
+    """Full-size batch: chunks are handed out dynamically and the two warps of a block share their queues, yet
+    every value must come out bit-identical on every run (no order-dependent reduction anywhere)."""
+    from ycr_b200.loss import v8SegmentationLoss
+    dev = _dev()
+    cfg, batch, feats = _c2(dev, seed=305)
+    crit = v8SegmentationLoss(nc=cfg.nc, nm=cfg.rays, strides=cfg.strides, device=dev)
+    ref = None
+    for _ in range(4):
+        fl = [f.clone().requires_grad_(True) for f in feats]
+        total, items = crit((fl, 5, 2), batch)
+        total.backward()
+        cur = (total.detach().clone(), items.clone(), [f.grad.clone() for f in fl])
+        if ref is None:
+            ref = cur
+            continue
+        assert torch.equal(ref[0], cur[0]) and torch.equal(ref[1], cur[1])
+        for a, b in zip(ref[2], cur[2]):
+            assert torch.equal(a, b)
