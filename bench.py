@@ -145,6 +145,24 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs NVML reports as local to its GPU before any pinned host buffer is allocated
+    (first touch then places the staging memory on that NUMA node: with one rank per GPU the host-to-device
+    copies of the e2e leg do not cross the socket interconnect).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_words = (os.cpu_count() + 63) // 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + bit for w, m in enumerate(masks) for bit in range(64) if (int(m) >> bit) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product)"
@@ -160,6 +178,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     use_dist = world > 1
+    if use_dist:   # (at N=1 the CPU baseline leg wants every host core)
+        bind_to_gpu_numa_node(local)
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
