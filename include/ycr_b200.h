@@ -100,6 +100,10 @@ typedef struct {
 
 const char* ycr_last_error(void);
 int ycr_version(void);
+/* sizeof of the seven structs of this header, in declaration order (grid, pred_view, gt, assign_cfg,
+ * assign_out, loss_cfg, nms_cfg): lets a foreign-language binding verify its mirror of the layouts.
+ * Returns 7. */
+int ycr_abi_sizes(int* sizes_out);
 
 /* Measurement hooks (bench.py): while enabled, every kernel of the path is bracketed by CUDA events on
  * the launching stream.  ycr_profile_end waits for them and returns, per kernel tag (YCR_T_* order:

@@ -30,6 +30,14 @@ def test_header_symbols_exported(lib):
     assert lib.ycr_version() == 100
 
 
+def test_struct_mirrors_match_the_library(lib):
+    """The ctypes mirrors of the seven ABI structs have the sizes the compiled library uses."""
+    sizes = (C.c_int * 7)()
+    assert lib.ycr_abi_sizes(sizes) == 7
+    mirrors = [L.Grid, L.PredView, L.Gt, L.AssignCfg, L.AssignOut, L.LossCfg, L.NmsCfg]
+    assert list(sizes) == [C.sizeof(m) for m in mirrors]
+
+
 def test_host_only_entry_points(lib):
     g = L.make_grid([(80, 80), (40, 40), (20, 20)], [8, 16, 32])
     boxes = torch.tensor([[100., 100., 260., 200.], [0., 0., 0., 0.], [10., 10., 630., 630.]])

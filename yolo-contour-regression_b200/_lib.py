@@ -61,6 +61,7 @@ class NmsCfg(C.Structure):
 EXPORTS = {
     "ycr_last_error": (C.c_char_p, []),
     "ycr_version": (C.c_int, []),
+    "ycr_abi_sizes": (C.c_int, [C.c_void_p]),
     "ycr_profile_begin": (C.c_int, [C.c_int]),
     "ycr_profile_select": (C.c_int, [C.c_uint]),
     "ycr_profile_end": (C.c_int, [C.c_void_p, C.c_void_p]),

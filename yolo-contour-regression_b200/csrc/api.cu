@@ -103,6 +103,14 @@ int ycr_profile_end(float* ms_sum, int* count) {
 }
 int ycr_version(void) { return 100; }
 
+int ycr_abi_sizes(int* sizes_out) {
+    if (!sizes_out) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    const size_t s[7] = {sizeof(ycr_grid_t), sizeof(ycr_pred_view_t), sizeof(ycr_gt_t), sizeof(ycr_assign_cfg_t),
+                         sizeof(ycr_assign_out_t), sizeof(ycr_loss_cfg_t), sizeof(ycr_nms_cfg_t)};
+    for (int i = 0; i < 7; ++i) sizes_out[i] = (int)s[i];
+    return 7;
+}
+
 int64_t ycr_candidate_bound_h(const ycr_grid_t* grid, const float* boxes_h, int64_t row_stride, int n_rows) {
     int64_t total = 0;
     for (int r = 0; r < n_rows; ++r) {
