@@ -101,6 +101,7 @@ __device__ __forceinline__ void axis_range(float lo_edge, float hi_edge, float s
 
 // Candidate rectangles, validity and candidate count of every GT (one thread per GT, any number of blocks).
 __global__ void __launch_bounds__(128) k_gt_rects(GridDev grid, ycr_gt_t gt, AssignWs ws) {
+    pdl_enter();
     const int BG = gt.B * gt.G;
     const int bg = blockIdx.x * 128 + threadIdx.x;
     if (bg >= BG) return;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(128) k_gt_rects(GridDev grid, ycr_gt_t gt, Ass
 // last phase lays out the order in which K1 draws the chunks: the full chunks of all GTs first, then the
 // partial chunk of every GT that has one - the cheapest work last keeps the tail of the persistent kernel short.
 __global__ void __launch_bounds__(1024) k_gt_setup(ycr_gt_t gt, AssignWs ws, int chunk) {
+    pdl_enter();
     __shared__ int s_wc[32], s_wk[32], s_wp[32];
     __shared__ int s_carry[3];
     __shared__ int s_n[1024], s_first[1024], s_po[1024];
@@ -236,6 +238,7 @@ __device__ __forceinline__ float align_of(float score, float ov, float alpha, fl
 
 template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
     // chunk descriptor of the current iteration: [0] first chunk of the GT, [1] its candidate count,
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
 // ------------------------------------------------------------------------------------------------
 #define K2_CACHE 2048   // align metrics of one GT kept in shared memory (per warp); larger GTs re-read L2
 __global__ void __launch_bounds__(128) k_topk_per_gt(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+    pdl_enter();
     __shared__ float s_al[4][K2_CACHE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bg = blockIdx.x * 4 + warp;
@@ -469,6 +473,7 @@ __global__ void __launch_bounds__(128) k_topk_per_gt(const __grid_constant__ Ass
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K3_NT) k_resolve_image(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                          int* n_pos_d) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A = a.grid.off[YCR_MAX_LEVELS];
     const int G = a.gt.G, topk = a.cfg.topk, pos_cap = ws.pos_cap;
@@ -662,6 +667,7 @@ struct PosArgs {
 template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                           const PosArgs pa) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
     const int bg = blockIdx.x, tid = threadIdx.x;
@@ -738,6 +744,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
 template <int R>
 __global__ void __launch_bounds__(256) k_positive_gather(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                          const PosArgs pa) {
+    pdl_enter();
     constexpr int NR = (R + 31) / 32;
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -916,7 +923,7 @@ static int launch_k1(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
     int dev = 0, sms = YCR_NUM_SMS;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    { YcrProfScope ps(YCR_T_CAND, st); k_cand_overlaps<R, K1_NT><<<sms * per_sm, K1_NT, smem, st>>>(a, ws); }
+    { YcrProfScope ps(YCR_T_CAND, st); YCR_CUDA_CHECK(ycr_launch(k_cand_overlaps<R, K1_NT>, dim3(sms * per_sm), dim3(K1_NT), smem, st, a, ws)); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -931,18 +938,18 @@ int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cu
     if (BG > 0) {
         {
             YcrProfScope ps(YCR_T_SETUP, st);
-            k_gt_rects<<<(BG + 127) / 128, 128, 0, st>>>(a.grid, a.gt, ws);
-            k_gt_setup<<<1, 1024, 0, st>>>(a.gt, ws, K1_NT);
+            YCR_CUDA_CHECK(ycr_launch(k_gt_rects, dim3((BG + 127) / 128), dim3(128), 0, st, a.grid, a.gt, ws));
+            YCR_CUDA_CHECK(ycr_launch(k_gt_setup, dim3(1), dim3(1024), 0, st, a.gt, ws, (int)K1_NT));
         }
         YCR_LAUNCH_CHECK();
         int rc = (a.cfg.rays == 36) ? launch_k1<36>(a, ws, st) : launch_k1<72>(a, ws, st);
         if (rc) return rc;
-        { YcrProfScope ps(YCR_T_TOPK, st); k_topk_per_gt<<<(BG + 3) / 4, 128, 0, st>>>(a, ws); }
+        { YcrProfScope ps(YCR_T_TOPK, st); YCR_CUDA_CHECK(ycr_launch(k_topk_per_gt, dim3((BG + 3) / 4), dim3(128), 0, st, a, ws)); }
         YCR_LAUNCH_CHECK();
     }
     const size_t smem3 = (size_t)G * YCR_MAX_LEVELS * 16 + (size_t)A * 4 + (size_t)ws.pos_cap * 16 + (size_t)G * 20 + 64;
     YCR_CUDA_CHECK(cudaFuncSetAttribute(k_resolve_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    { YcrProfScope ps(YCR_T_RESOLVE, st); k_resolve_image<<<B, K3_NT, smem3, st>>>(a, ws, n_pos_d); }
+    { YcrProfScope ps(YCR_T_RESOLVE, st); YCR_CUDA_CHECK(ycr_launch(k_resolve_image, dim3(B), dim3(K3_NT), smem3, st, a, ws, n_pos_d)); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -958,19 +965,19 @@ int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_d
     YcrProfScope ps(YCR_T_POS, st);
     if (ws.cand_t) {
         dim3 grid((ws.pos_cap + 7) / 8, B);
-        if (a.cfg.rays == 36) k_positive_gather<36><<<grid, 256, 0, st>>>(a, ws, pa);
-        else k_positive_gather<72><<<grid, 256, 0, st>>>(a, ws, pa);
+        if (a.cfg.rays == 36) YCR_CUDA_CHECK(ycr_launch(k_positive_gather<36>, grid, dim3(256), 0, st, a, ws, pa));
+        else YCR_CUDA_CHECK(ycr_launch(k_positive_gather<72>, grid, dim3(256), 0, st, a, ws, pa));
         YCR_LAUNCH_CHECK();
         return YCR_OK;
     }
     if (a.cfg.rays == 36) {
         const size_t smem = sizeof(PolarSmem<36, K4_NT>);
         YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_positive_targets<36, K4_NT><<<BG, K4_NT, smem, st>>>(a, ws, pa);
+        YCR_CUDA_CHECK(ycr_launch(k_positive_targets<36, K4_NT>, dim3(BG), dim3(K4_NT), smem, st, a, ws, pa));
     } else {
         const size_t smem = sizeof(PolarSmem<72, K4_NT>);
         YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<72, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_positive_targets<72, K4_NT><<<BG, K4_NT, smem, st>>>(a, ws, pa);
+        YCR_CUDA_CHECK(ycr_launch(k_positive_targets<72, K4_NT>, dim3(BG), dim3(K4_NT), smem, st, a, ws, pa));
     }
     YCR_LAUNCH_CHECK();
     return YCR_OK;

@@ -1,5 +1,7 @@
 // Shared declarations for the sm_100a kernels of the polar-contour hot path.
 #pragma once
+#include <utility>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -18,6 +20,36 @@ enum { YCR_T_SETUP = 0, YCR_T_CAND = 1, YCR_T_TOPK = 2, YCR_T_RESOLVE = 3, YCR_T
        YCR_T_FINAL = 6, YCR_T_DECODE = 7, YCR_T_NMS_FILTER = 8, YCR_T_NMS_SORT = 9, YCR_T_NMS_SUPPRESS = 10,
        YCR_T_COUNT = 16 };
 void ycr_prof_mark(int tag, int end, cudaStream_t st);
+
+// Programmatic dependent launch (sm_90+): the kernels of the training path are launched with
+// programmaticStreamSerializationAllowed, execute pdl_enter() as their first statement - wait until the
+// preceding grid in the stream has completed and its writes are visible, then allow the next grid to be
+// launched - so the launch and block scheduling of kernel N+1 overlap the tail of kernel N instead of following
+// it.  YCR_PDL=0 in the environment turns the attribute off (plain stream order; pdl_enter is then a no-op).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+inline bool ycr_pdl_enabled() {
+    static const int on = [] { const char* e = getenv("YCR_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t ycr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ycr_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 struct YcrProfScope {
     int tag; cudaStream_t st;
     YcrProfScope(int t, cudaStream_t s) : tag(t), st(s) { ycr_prof_mark(tag, 0, st); }

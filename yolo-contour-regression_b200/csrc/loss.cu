@@ -11,6 +11,7 @@
 __global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                        const float* f0, const float* f1, const float* f2, const float* f3,
                                                        float* g0, float* g1, float* g2, float* g3, float cls_gain) {
+    pdl_enter();
     __shared__ float s_red[K5_NT / 32];
     const int A = a.grid.off[YCR_MAX_LEVELS];
     const int b = blockIdx.y;
@@ -92,6 +93,7 @@ __device__ __forceinline__ float bce_term(float x, float t, float gscale, float&
 __global__ void __launch_bounds__(K5_NT, K5_MINB) k_loss_stream_v4(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                           const float* f0, const float* f1, const float* f2, const float* f3,
                                                           float* g0, float* g1, float* g2, float* g3, float cls_gain) {
+    pdl_enter();
     __shared__ float s_red[K5_NT / 32];
     const int A = a.grid.off[YCR_MAX_LEVELS];
     const int b = blockIdx.y;
@@ -171,6 +173,7 @@ YCR_PRAGMA_UNROLL(K5_UNROLL)
 // warp w sums images w, w+32, ... and partials w, w+32.., then one fixed tree over the 32 warps.
 __global__ void __launch_bounds__(1024) k_loss_finalize(AssignWs ws, int B, int n_bce, float box_gain, float cls_gain,
                                                         float* loss_out) {
+    pdl_enter();
     __shared__ double s_b[32], s_p[32];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     double sb = 0.0, sp = 0.0;
@@ -221,15 +224,15 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* con
         dim3 grid((A / 4 + K5_NT - 1) / K5_NT, B);
         nblk = (int)(grid.x * grid.y);
         YcrProfScope ps(YCR_T_STREAM, st);
-        k_loss_stream_v4<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain);
+        YCR_CUDA_CHECK(ycr_launch(k_loss_stream_v4, grid, dim3(K5_NT), 0, st, a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain));
     } else {
         dim3 grid((A + K5_NT - 1) / K5_NT, B);
         nblk = (int)(grid.x * grid.y);
         YcrProfScope ps(YCR_T_STREAM, st);
-        k_loss_stream<<<grid, K5_NT, 0, st>>>(a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain);
+        YCR_CUDA_CHECK(ycr_launch(k_loss_stream, grid, dim3(K5_NT), 0, st, a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain));
     }
     YCR_LAUNCH_CHECK();
-    { YcrProfScope ps(YCR_T_FINAL, st); k_loss_finalize<<<1, 1024, 0, st>>>(ws, B, nblk, lcfg.box_gain, lcfg.cls_gain, loss_out); }
+    { YcrProfScope ps(YCR_T_FINAL, st); YCR_CUDA_CHECK(ycr_launch(k_loss_finalize, dim3(1), dim3(1024), 0, st, ws, B, nblk, lcfg.box_gain, lcfg.cls_gain, loss_out)); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -240,6 +243,7 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* con
 struct ScaleArgs { float* p[YCR_MAX_LEVELS]; int64_t n[YCR_MAX_LEVELS]; int n_levels; };
 
 __global__ void __launch_bounds__(256) k_scale(const ScaleArgs sa, const float* scale) {
+    pdl_enter();
     const float s = *scale;
     if (s == 1.f) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -253,7 +257,7 @@ int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* s
     for (int l = 0; l < n_levels && l < YCR_MAX_LEVELS; ++l)
         if (n[l] > 0) { sa.p[sa.n_levels] = p[l]; sa.n[sa.n_levels] = n[l]; ++sa.n_levels; }
     if (sa.n_levels == 0) return YCR_OK;
-    k_scale<<<YCR_NUM_SMS * 2, 256, 0, st>>>(sa, scale);
+    YCR_CUDA_CHECK(ycr_launch(k_scale, dim3(YCR_NUM_SMS * 2), dim3(256), 0, st, sa, scale));
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
