@@ -196,6 +196,11 @@ int ycr_bbox_loss_fwd_bwd(const float* pred_dist, const float* pred_bboxes, cons
  * feats -> allpred (B, 4+nc+3R, A) = [box xyxy | sigmoid cls | x_0.. | y_0.. | valid_0..]. */
 int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred,
                void* stream);
+/* Same, and also writes per anchor the best class as {float score, int class} pairs (B, A, 8 bytes; first
+ * maximum, i.e. `cls.max(1)` of utils/ops.py:386; class -1 = not provided).  Passed to ycr_nms through
+ * ycr_nms_cfg_t.best_class it saves single-label NMS the read of all class rows. */
+int ycr_decode_best(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred,
+                    void* best_class_out, void* stream);
 
 typedef struct {
     float conf_thres, iou_thres;
@@ -205,6 +210,7 @@ typedef struct {
     const int* classes; int n_classes; /* optional device list of class ids to keep, utils/ops.py:390 */
     int compact_rows;   /* 0: image b's rows start at out_rows[b*max_det]; 1: rows of all images back to back
                          * (image b starts at row sum(out_counts[0..b-1])), so the host can split one tensor */
+    const void* best_class; /* optional: what ycr_decode_best wrote for THIS prediction tensor, else NULL */
 } ycr_nms_cfg_t;
 
 size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* cfg);

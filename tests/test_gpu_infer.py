@@ -193,3 +193,36 @@ def test_nms_padded_and_compact_row_layouts_agree():
     for b in range(B):
         assert torch.equal(rows[b, :n[b]], ref[b])
         assert bool((rows[b, n[b]:] == -1.0).all())            # nothing written beyond the kept rows
+
+
+@pytest.mark.parametrize("imgsz", [384, 320])   # 320: a 10-wide level, the scalar decode provides no by-product
+def test_nms_uses_the_decode_by_product_only_when_valid(imgsz):
+    """head.decode leaves the per-anchor best class on its output tensor; non_max_suppression starts from it
+    when it is handed that very tensor, unmodified - and must not when the tensor was changed in place or is
+    another object.  All three routes have to agree with a plain scan of the class rows."""
+    from ycr_b200 import synth
+    from ycr_b200.head import decode
+    from ycr_b200.ops import non_max_suppression
+    dev = _dev()
+    cfg = synth.PathConfig("h", 4, 0, imgsz, rays=36, nc=12)
+    feats = [f.to(dev) for f in synth.make_feats(cfg, 77)]
+    out = decode(feats, cfg.strides, cfg.nc, cfg.rays)
+    assert getattr(out, "_ycr_best_class", None) is not None
+    best, ver, nc = out._ycr_best_class
+    conf, j = out[:, 4:4 + cfg.nc].max(1)                       # what utils/ops.py:386 computes
+    if imgsz == 384:
+        assert torch.equal(best[..., 0].view(torch.float32), conf) and torch.equal(best[..., 1].long(), j)
+    else:
+        assert bool((best[..., 1] == -1).all())                   # "not provided": NMS scans the class rows
+    with_hint = non_max_suppression(out, 0.25, 0.6, nc=cfg.nc)
+    plain = non_max_suppression(out.clone(), 0.25, 0.6, nc=cfg.nc)          # a copy carries no by-product
+    assert sum(d.shape[0] for d in plain) > 0
+    for a, b in zip(with_hint, plain):
+        assert torch.equal(a, b)
+    out[:, 4:4 + cfg.nc] *= 0.5                                   # in place: the by-product is stale now
+    stale = non_max_suppression(out, 0.25, 0.6, nc=cfg.nc)
+    fresh = non_max_suppression(out.clone(), 0.25, 0.6, nc=cfg.nc)
+    assert [d.shape[0] for d in stale] == [d.shape[0] for d in fresh]
+    for a, b in zip(stale, fresh):
+        assert torch.equal(a, b)
+    assert [d.shape[0] for d in fresh] != [d.shape[0] for d in plain]    # (the change did matter)

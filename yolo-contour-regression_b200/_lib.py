@@ -55,7 +55,8 @@ class LossCfg(C.Structure):
 class NmsCfg(C.Structure):
     _fields_ = [("conf_thres", C.c_float), ("iou_thres", C.c_float), ("agnostic", C.c_int),
                 ("multi_label", C.c_int), ("max_det", C.c_int), ("nc", C.c_int), ("max_nms", C.c_int),
-                ("max_wh", C.c_float), ("classes", C.c_void_p), ("n_classes", C.c_int), ("compact_rows", C.c_int)]
+                ("max_wh", C.c_float), ("classes", C.c_void_p), ("n_classes", C.c_int), ("compact_rows", C.c_int),
+                ("best_class", C.c_void_p)]
 
 
 EXPORTS = {
@@ -82,6 +83,8 @@ EXPORTS = {
     "ycr_bbox_loss_fwd_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]),
     "ycr_decode": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
                              C.c_void_p]),
+    "ycr_decode_best": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "ycr_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg)]),
     "ycr_nms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg), C.c_void_p, C.c_void_p,
                           C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -44,7 +44,8 @@ int launch_bbox_loss(const float* pred_dist, const float* pred_bboxes, const flo
 int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* scale, cudaStream_t st);
 int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
                         cudaStream_t st);
-int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, cudaStream_t st);
+int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, int2* best,
+                  cudaStream_t st);
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg);
 int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
                void* workspace, size_t workspace_bytes, cudaStream_t st);
@@ -230,7 +231,15 @@ int ycr_bbox_loss_fwd_bwd(const float* pred_dist, const float* pred_bboxes, cons
 int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, void* stream) {
     if (!grid || !feats || !allpred) { ycr_set_error("null argument"); return YCR_E_ARG; }
     if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
-    return launch_decode(grid, feats, B, nc, R, allpred, reinterpret_cast<cudaStream_t>(stream));
+    return launch_decode(grid, feats, B, nc, R, allpred, nullptr, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ycr_decode_best(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred,
+                    void* best_class_out, void* stream) {
+    if (!grid || !feats || !allpred || !best_class_out) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
+    return launch_decode(grid, feats, B, nc, R, allpred, reinterpret_cast<int2*>(best_class_out),
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* cfg) {

@@ -23,9 +23,15 @@ def decode(feats, strides, nc: int, R: int = 36):
     shapes = [tuple(f.shape[2:]) for f in feats]
     A = sum(h * w for h, w in shapes)
     out = torch.empty(B, 4 + nc + 3 * R, A, device=feats[0].device, dtype=torch.float32)
+    # per anchor {best class score, best class}: a by-product of the class pass that single-label NMS starts
+    # from.  It rides on the output tensor; ops.non_max_suppression uses it only if the tensor it is handed is
+    # this very object and no in-place operation has touched it since (version counter).
+    best = torch.empty(B, A, 2, device=feats[0].device, dtype=torch.int32)
     cgrid = L.make_grid(shapes, [float(s) for s in strides])
-    rc = L.lib().ycr_decode(C.byref(cgrid), L.ptr_array(feats), B, nc, R, out.data_ptr(), L.stream_ptr(out.device))
-    L.check(rc, "ycr_decode")
+    rc = L.lib().ycr_decode_best(C.byref(cgrid), L.ptr_array(feats), B, nc, R, out.data_ptr(), best.data_ptr(),
+                                 L.stream_ptr(out.device))
+    L.check(rc, "ycr_decode_best")
+    out._ycr_best_class = (best, out._version, nc)
     return out
 
 

@@ -57,13 +57,21 @@ def non_max_suppression(
     nbytes = lib.ycr_nms_workspace_bytes(B, A, CH, C.byref(cfg))
     ws = L.Workspace.get("nms", nbytes, dev)
     cfg.compact_rows = 1   # rows of all images back to back: one split instead of B Python slices
+    hint = getattr(prediction, "_ycr_best_class", None)   # left by head.decode on its own output tensor
+    best_t = None
+    if (hint is not None and pred is prediction and not cfg.multi_label and hint[1] == prediction._version
+            and hint[2] == nc and tuple(hint[0].shape) == (B, A, 2)):
+        best_t = hint[0]
+        cfg.best_class = best_t.data_ptr()
+    else:
+        cfg.best_class = None
     rows = torch.empty(B * max_det, 6 + nm, device=dev, dtype=torch.float32)
     counts = torch.empty(B, device=dev, dtype=torch.int32)
     rc = lib.ycr_nms(pred.data_ptr(), B, CH, A, C.byref(cfg), rows.data_ptr(), counts.data_ptr(), ws.data_ptr(),
                      ws.numel(), L.stream_ptr(dev))
     L.check(rc, "ycr_nms")
     n = counts.tolist()
-    del cls_t
+    del cls_t, best_t
     return list(torch.split(rows[:sum(n)], n))
 
 
