@@ -11,6 +11,12 @@
 #ifndef K1_NT
 #define K1_NT 64
 #endif
+#ifndef K1_NT_NARROW
+#define K1_NT_NARROW 32   // 72 rays: 1.2 KB of lists per thread - one-warp blocks fit five per SM (two-warp blocks: two)
+#endif
+// threads per block of K1 = candidates per chunk, by ray count
+static inline int k1_nt(int R) { return (R > 36) ? K1_NT_NARROW : K1_NT; }
+template <int R> struct K1Nt { static constexpr int value = (R > 36) ? K1_NT_NARROW : K1_NT; };
 #ifndef K1_SHARE_QUEUES
 #define K1_SHARE_QUEUES 1
 #endif
@@ -771,14 +777,15 @@ __global__ void __launch_bounds__(256) k_positive_gather(const __grid_constant__
     const int grow = pa.img_base[b] + row;
     const int ci = ws.valid[bg] ? cand_index(a.grid, ws.rect + bg * YCR_MAX_LEVELS, ap) : -1;
     const float* tp = nullptr;
-    if (ci >= 0) tp = ws.cand_t + ((int64_t)(ws.chunk_off[bg] + ci / K1_NT) * R) * K1_NT + (ci % K1_NT);
+    constexpr int NT1 = K1Nt<R>::value;
+    if (ci >= 0) tp = ws.cand_t + ((int64_t)(ws.chunk_off[bg] + ci / NT1) * R) * NT1 + (ci % NT1);
     float t[NR];
     float tmin = 3.4e38f, tmax = 0.f, smin = 0.f, smax = 0.f;
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
         const int i = lane + 32 * k;
         if (i < R) {
-            t[k] = tp ? tp[i * K1_NT] : YCR_FLOOR;
+            t[k] = tp ? tp[i * NT1] : YCR_FLOOR;
             tmin = fminf(tmin, t[k]);
             tmax = fmaxf(tmax, t[k]);
             smin += fmaxf(fminf(p[k], t[k]), YCR_FLOOR);
@@ -872,7 +879,8 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
     w.ncand = al.take<int>(BG + 1);
     w.cand_off = al.take<int>(BG + 1);
     w.chunk_off = al.take<int>(BG + 1);
-    const size_t chunks_cap = (size_t)cand_cap / K1_NT + (size_t)BG + 1;  // every GT adds at most one partial chunk
+    const size_t nt1 = (size_t)k1_nt(R);
+    const size_t chunks_cap = (size_t)cand_cap / nt1 + (size_t)BG + 1;  // every GT adds at most one partial chunk
     w.chunk_bg = al.take<int>(chunks_cap);
     w.chunk_work = al.take<int>(chunks_cap);
     w.part_off = al.take<int>(BG + 1);
@@ -887,8 +895,8 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
         // a gather instead of a second sweep.  YCR_T_STORE_MAX_BYTES overrides the 1 GiB budget (0 = never).
         const char* env = getenv("YCR_T_STORE_MAX_BYTES");
         const size_t budget = env ? (size_t)strtoull(env, nullptr, 10) : ((size_t)1 << 30);
-        const size_t bytes = chunks_cap * R * K1_NT * sizeof(float);
-        w.cand_t = (bytes <= budget && BG > 0) ? al.take<float>(chunks_cap * R * K1_NT) : nullptr;
+        const size_t bytes = chunks_cap * R * nt1 * sizeof(float);
+        w.cand_t = (bytes <= budget && BG > 0) ? al.take<float>(chunks_cap * R * nt1) : nullptr;
     }
     w.sel = al.take<int>((size_t)BG * topk + 1);
     w.npos = al.take<int>(B + 1);
@@ -915,15 +923,16 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
 
 template <int R>
 static int launch_k1(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
-    const size_t smem = sizeof(PolarSmem<R, K1_NT>);
-    YCR_CUDA_CHECK(cudaFuncSetAttribute(k_cand_overlaps<R, K1_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int NT1 = K1Nt<R>::value;
+    const size_t smem = sizeof(PolarSmem<R, NT1>);
+    YCR_CUDA_CHECK(cudaFuncSetAttribute(k_cand_overlaps<R, NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    YCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cand_overlaps<R, K1_NT>, K1_NT, smem));
+    YCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cand_overlaps<R, NT1>, NT1, smem));
     if (per_sm < 1) per_sm = 1;
     int dev = 0, sms = YCR_NUM_SMS;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    { YcrProfScope ps(YCR_T_CAND, st); YCR_CUDA_CHECK(ycr_launch(k_cand_overlaps<R, K1_NT>, dim3(sms * per_sm), dim3(K1_NT), smem, st, a, ws)); }
+    { YcrProfScope ps(YCR_T_CAND, st); YCR_CUDA_CHECK(ycr_launch(k_cand_overlaps<R, NT1>, dim3(sms * per_sm), dim3(NT1), smem, st, a, ws)); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -939,7 +948,7 @@ int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cu
         {
             YcrProfScope ps(YCR_T_SETUP, st);
             YCR_CUDA_CHECK(ycr_launch(k_gt_rects, dim3((BG + 127) / 128), dim3(128), 0, st, a.grid, a.gt, ws));
-            YCR_CUDA_CHECK(ycr_launch(k_gt_setup, dim3(1), dim3(1024), 0, st, a.gt, ws, (int)K1_NT));
+            YCR_CUDA_CHECK(ycr_launch(k_gt_setup, dim3(1), dim3(1024), 0, st, a.gt, ws, k1_nt(a.cfg.rays)));
         }
         YCR_LAUNCH_CHECK();
         int rc = (a.cfg.rays == 36) ? launch_k1<36>(a, ws, st) : launch_k1<72>(a, ws, st);
