@@ -62,7 +62,10 @@ typedef struct {
 /* Padded ground truth, as v8DetectionLoss.preprocess emits it (utils/loss.py:215-239) and
  * v8SegmentationLoss splits it (utils/loss.py:842-844).  Row (b,g) of each field lives at
  * ptr[(b*G + g) * row_stride]; the split views of the packed (B,G,725) tensor have row_stride 725.
- * mask_gt may be NULL, in which case valid(b,g) = (sum of the 4 box values > 0), utils/loss.py:844. */
+ * mask_gt may be NULL, in which case valid(b,g) = (sum of the 4 box values > 0), utils/loss.py:844.
+ * Limits (YCR_E_ARG beyond them, with the numbers in ycr_last_error()): the per-image resolution step keeps
+ * 4*A + 244*G bytes (topk = 10) in shared memory, at most 227 KB: G <= 815 GTs per image at A = 8400 (640 px),
+ * G <= 401 at A = 33600 (1280 px); G <= 65535 always. */
 typedef struct {
     int B, G;
     const float* labels; int64_t labels_stride; /* 1 value: class id as float */
@@ -74,7 +77,7 @@ typedef struct {
 /* Assigner hyper-parameters, TaskAlignedAssigner.__init__ (utils/tal.py:1125); the live values are
  * topk=10, alpha=0.5, beta=4.0 (utils/loss.py:210). */
 typedef struct {
-    int topk;
+    int topk;        /* 1..64 */
     int num_classes;
     int rays; /* 36 (reference) or 72 */
     float alpha, beta, eps;

@@ -55,7 +55,19 @@ static int check_common(const ycr_grid_t* grid, const ycr_assign_cfg_t* cfg, int
     if (grid->n_levels < 1 || grid->n_levels > YCR_MAX_LEVELS) { ycr_set_error("n_levels %d out of range", grid->n_levels); return YCR_E_ARG; }
     if (cfg->rays != 36 && cfg->rays != 72) { ycr_set_error("rays must be 36 or 72, got %d", cfg->rays); return YCR_E_ARG; }
     if (cfg->topk < 1 || cfg->topk > 64) { ycr_set_error("topk %d out of range [1,64]", cfg->topk); return YCR_E_ARG; }
-    if (B < 1 || G < 0 || G > 255) { ycr_set_error("B=%d G=%d out of range (G<=255)", B, G); return YCR_E_ARG; }
+    if (B < 1 || G < 0 || G > 65535) { ycr_set_error("B=%d G=%d out of range", B, G); return YCR_E_ARG; }
+    {
+        // the per-image resolution kernel keeps the image's anchors, GT descriptors and positives in shared memory
+        int64_t A = 0;
+        for (int l = 0; l < grid->n_levels; ++l) A += (int64_t)grid->h[l] * grid->w[l];
+        const int64_t need = ycr_resolve_smem_bytes(A, G, cfg->topk);
+        if (need > YCR_SMEM_MAX) {
+            ycr_set_error("%d GTs per image with %lld anchors and topk %d need %lld bytes of shared memory per image "
+                          "(limit %d): lower the number of instances per image", G, (long long)A, cfg->topk, (long long)need,
+                          YCR_SMEM_MAX);
+            return YCR_E_ARG;
+        }
+    }
     return YCR_OK;
 }
 
@@ -151,7 +163,7 @@ int ycr_assign(const ycr_grid_t* grid, const ycr_pred_view_t* pred, const ycr_gt
     a.pred = *pred;
     a.gt = *gt;
     a.cfg = *cfg;
-    a.pc = make_polar_const(cfg->rays);
+    a.ac = make_arc_const(cfg->rays);
     AssignWs ws;
     const size_t need = assign_ws_layout(&ws, workspace, a.grid, gt->B, gt->G, cfg->topk, cfg->rays, cand_capacity, false);
     if (need > workspace_bytes) { ycr_set_error("assign workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
@@ -171,7 +183,7 @@ int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, floa
     a.grid = make_grid_dev(grid);
     a.gt = *gt;
     a.cfg = *acfg;
-    a.pc = make_polar_const(acfg->rays);
+    a.ac = make_arc_const(acfg->rays);
     const int R = acfg->rays, nc = acfg->num_classes;
     for (int l = 0; l < grid->n_levels; ++l) {
         const int64_t hw = (int64_t)grid->h[l] * grid->w[l];

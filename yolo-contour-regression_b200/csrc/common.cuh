@@ -12,6 +12,12 @@
 #define YCR_FLOOR 1e-6f          // utils/tal.py:1189-1191,1275-1277,1455; nn/modules/head.py:480
 #define YCR_GATE_DEG 3.0         // utils/tal.py:1185,1270
 #define YCR_NUM_SMS 148
+#define YCR_SMEM_MAX 232448      // 227 KB: opt-in shared memory per block on sm_100
+// shared memory of k_resolve_image: [G][levels] rectangles, [A] pick words, 4 arrays of G*topk, 5 arrays of G
+static inline int64_t ycr_resolve_smem_bytes(int64_t A, int64_t G, int64_t topk) {
+    const int64_t pos_cap = (G * topk > 0) ? G * topk : 1;
+    return G * YCR_MAX_LEVELS * 16 + A * 4 + pos_cap * 16 + G * 20 + 64;
+}
 
 void ycr_set_error(const char* fmt, ...);
 

@@ -50,6 +50,7 @@ class _SegLossFn(torch.autograd.Function):
                                       loss_out.data_ptr(), ws.data_ptr(), ws.numel(), cand_cap, L.stream_ptr(dev))
         L.check(rc, "ycr_seg_loss_fwd_bwd")
         ctx.grads = grads
+        ctx.scaled = False
         ctx.cgrid = cgrid
         ctx.channels = feats[0].shape[1]
         ctx.B = B
@@ -63,6 +64,12 @@ class _SegLossFn(torch.autograd.Function):
             return (None, None, None) + (None,) * 3
         dev = grads[0].device
         g = g_total.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if ctx.scaled:
+            # a second backward through the same graph (retain_graph=True): the stored maps already carry the
+            # first upstream gradient and would be scaled twice
+            raise RuntimeError("v8SegmentationLoss: backward through the same loss twice is not supported "
+                               "(the gradient maps are produced once, by the forward kernel)")
+        ctx.scaled = True
         rc = L.lib().ycr_scale_grads(C.byref(ctx.cgrid), ctx.B, ctx.channels, L.ptr_array(grads), g.data_ptr(),
                                      L.stream_ptr(dev))
         L.check(rc, "ycr_scale_grads")
@@ -170,7 +177,9 @@ class v8SegmentationLoss:
         img_hw = (feats[0].shape[2] * self.stride_list[0], feats[0].shape[3] * self.stride_list[0])
         try:
             packed, cap = self.pack_targets(batch, B, img_hw)
-        except RuntimeError as e:  # same re-wrap as utils/loss.py:850-856
+        except L.YcrError:   # a missing library or a failed CUDA call is not a dataset problem
+            raise
+        except RuntimeError as e:  # same re-wrap as utils/loss.py:850-856 (cat / view of malformed rows)
             raise TypeError("ERROR segment dataset incorrectly formatted or not a segment dataset.") from e
         gt_labels, gt_boxes, gt_coor = packed.split((1, 4, 720), 2)
         gt, keep = gt_struct(gt_labels, gt_boxes, gt_coor, None)

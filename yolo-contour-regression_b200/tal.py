@@ -84,27 +84,23 @@ class TaskAlignedAssigner(nn.Module):
         if st.numel() != A or xs.numel() != A:
             raise ValueError("anc_points / stride_tensor do not describe the anchors of pd_scores")
         cuts = [0] + (torch.nonzero(st[1:] != st[:-1]).flatten() + 1).tolist() + [A]
-        key = (A, tuple(cuts))
-        g = self._grid_cache.get(key)
-        if g is None:
-            shapes, strides = [], []
-            for lo, hi in zip(cuts[:-1], cuts[1:]):
-                x = xs[lo:hi]
-                wrap = torch.nonzero(x[1:] <= x[:-1]).flatten()
-                w = int(wrap[0]) + 1 if wrap.numel() else hi - lo
-                if (hi - lo) % w:
-                    raise ValueError("anchor layout is not the make_anchors_polar grid")
-                shapes.append(((hi - lo) // w, w))
-                strides.append(float(st[lo]))
-            g = (shapes, strides)
-            self._grid_cache[key] = g
-        return g
+        # (no cache: two grids with the same anchor counts per level can differ in width, e.g. 80x60 and 60x80)
+        shapes, strides = [], []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            x = xs[lo:hi]
+            wrap = torch.nonzero(x[1:] <= x[:-1]).flatten()
+            w = int(wrap[0]) + 1 if wrap.numel() else hi - lo
+            if (hi - lo) % w:
+                raise ValueError("anchor layout is not the make_anchors_polar grid")
+            shapes.append(((hi - lo) // w, w))
+            strides.append(float(st[lo]))
+        return shapes, strides
 
     def _grid(self, ss, imgsz, A):
-        key = (A, tuple(int(s.shape[0]) for s in ss))
+        hw = [float(v) for v in (imgsz.tolist() if torch.is_tensor(imgsz) else imgsz)]
+        key = (A, tuple(int(s.shape[0]) for s in ss), tuple(hw))   # the image size fixes the level widths
         g = self._grid_cache.get(key)
         if g is None:
-            hw = [float(v) for v in (imgsz.tolist() if torch.is_tensor(imgsz) else imgsz)]
             strides = [float(s.flatten()[0]) for s in ss]
             shapes = []
             for s, st in zip(ss, strides):
