@@ -117,7 +117,8 @@ int ycr_profile_begin(int max_records);
  * carry the events of its dominant kernel only. */
 int ycr_profile_select(unsigned tag_mask);
 int ycr_profile_end(float* ms_sum_h, int* count_h);
-/* Work counters of the candidate kernel since the last reset (synchronises the device):
+/* Work counters of the candidate kernel since the last reset (synchronises the device); all zero unless the
+ * library was built with -DYCR_STATS=1 (measurement build: YCR_NVCC_FLAGS in build.py):
  * out_h[0] candidates swept, [1] (candidate,ray) pairs the own angular bin could not settle,
  * [2] pairs that needed the exact 360-point scan, [3] reserved. */
 int ycr_debug_stats(unsigned long long* out_h, int reset);

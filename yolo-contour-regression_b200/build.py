@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "assign.cu", "loss.cu", "infer.cu", "bbox_loss.cu", "resample.cu"]
-HEADERS = ["common.cuh", "polar_arcs.cuh", "train_path.cuh"]
+HEADERS = ["common.cuh", "polar_core.cuh", "train_path.cuh"]
 OUT = os.path.join(_HERE, "lib", "libycr_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]
@@ -26,7 +26,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    extra = os.environ.get("YCR_NVCC_FLAGS", "").split()   # e.g. -DYCR_STATS=1 for the measurement build
+    cmd = [nvcc] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
           [os.path.join(_HERE, "csrc", s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -163,7 +163,7 @@ int ycr_assign(const ycr_grid_t* grid, const ycr_pred_view_t* pred, const ycr_gt
     a.pred = *pred;
     a.gt = *gt;
     a.cfg = *cfg;
-    a.ac = make_arc_const(cfg->rays);
+    a.pc = make_polar_const(cfg->rays);
     AssignWs ws;
     const size_t need = assign_ws_layout(&ws, workspace, a.grid, gt->B, gt->G, cfg->topk, cfg->rays, cand_capacity, false);
     if (need > workspace_bytes) { ycr_set_error("assign workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
@@ -183,7 +183,7 @@ int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, floa
     a.grid = make_grid_dev(grid);
     a.gt = *gt;
     a.cfg = *acfg;
-    a.ac = make_arc_const(acfg->rays);
+    a.pc = make_polar_const(acfg->rays);
     const int R = acfg->rays, nc = acfg->num_classes;
     for (int l = 0; l < grid->n_levels; ++l) {
         const int64_t hw = (int64_t)grid->h[l] * grid->w[l];

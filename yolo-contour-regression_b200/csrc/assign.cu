@@ -8,10 +8,26 @@
 #include "train_path.cuh"
 #include <stdlib.h>
 
-// Candidates per chunk = threads per block of K1: one-warp blocks need no barrier partner.
-static inline int k1_nt(int) { return 32; }
-template <int R> struct K1Nt { static constexpr int value = 32; };
+// Candidates per chunk = threads per block of K1.  One-warp blocks (nine per SM at 36 rays) need no barrier
+// partner and no queue sharing and measure 0.6 % faster than two-warp blocks (five per SM, queues shared
+// between the warps); -DK1_NT=64 selects the latter.
+#ifndef K1_NT
+#define K1_NT 32
+#endif
+#ifndef K1_NT_NARROW
+#define K1_NT_NARROW 32   // 72 rays: 1.2 KB of lists per thread - one-warp blocks fit five per SM (two-warp blocks: two)
+#endif
+// threads per block of K1 = candidates per chunk, by ray count
+static inline int k1_nt(int R) { return (R > 36) ? K1_NT_NARROW : K1_NT; }
+template <int R> struct K1Nt { static constexpr int value = (R > 36) ? K1_NT_NARROW : K1_NT; };
+#ifndef K1_SHARE_QUEUES
+#define K1_SHARE_QUEUES 1
+#endif
+#ifndef YCR_STATS
+#define YCR_STATS 0
+#endif
 #define K3_NT 512
+#define K4_NT 32   // positives per GT are ~topk: one warp per block
 
 // running totals since the last ycr_debug_stats(reset): candidates, pairs queued for neighbourhood
 // settlement, pairs that needed the exact scan (measurement aid, three atomics per block iteration)
@@ -213,13 +229,15 @@ __global__ void __launch_bounds__(1024) k_gt_setup(ycr_gt_t gt, AssignWs ws, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: one thread per in-box candidate (b,g,a): polar targets (polar_arcs.cuh), Polar-IoU (MaskIOU
-// utils/tal.py:1445), align metric score^alpha * ov^beta (utils/tal.py:1281).  Persistent one-warp blocks
-// draw chunks of 32 candidates of one GT from a global counter.
+// K1: one thread per in-box candidate (b,g,a): polar targets, Polar-IoU (MaskIOU utils/tal.py:1445),
+// align metric score^alpha * ov^beta (utils/tal.py:1281).  Persistent blocks walk the chunk list.
 // ------------------------------------------------------------------------------------------------
 template <int R, int NT>
-__device__ __forceinline__ void init_raydir(ArcSmem<R, NT>& sm, int tid) {
-    for (int i = tid; i <= R; i += NT) arc_init_raydir_entry<R, NT>(sm, i);
+__device__ __forceinline__ void init_raydir(PolarSmem<R, NT>& sm, int tid) {
+    for (int i = tid; i < R; i += NT) {
+        const double ang = (double)(i * (360 / R)) * (3.14159265358979323846 / 180.0);
+        sm.raydir[i] = make_float2((float)cos(ang), (float)sin(ang));
+    }
 }
 
 __device__ __forceinline__ float align_of(float score, float ov, float alpha, float beta) {
@@ -230,29 +248,29 @@ __device__ __forceinline__ float align_of(float score, float ov, float alpha, fl
     return s * o;
 }
 
-template <int R>
-__global__ void __launch_bounds__(32) k_cand_arcs(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
+template <int R, int NT>
+__global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws) {
     pdl_enter();
-    constexpr int NT = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ArcSmem<R, NT>& sm = *reinterpret_cast<ArcSmem<R, NT>*>(smem_raw);
+    PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
     // chunk descriptor of the current iteration: [0] first chunk of the GT, [1] its candidate count,
     // [2] chunk index, [3] GT index, [4..] the GT's candidate rectangles (int4 per level)
     __shared__ __align__(16) int s_desc[4 + 4 * YCR_MAX_LEVELS];
+    __shared__ int s_ctl[6];   // queue sharing between the two warps (polar_settle_queue_shared)
     static_assert(4 + 4 * YCR_MAX_LEVELS <= 32, "descriptor is fetched by one warp, one word per lane");
-    constexpr int CW = (2 * YCR_C + 31) / 32;   // contour words per lane
+    constexpr int CW = (2 * YCR_C + 31) / 32;   // contour words per lane of warp 0
     const int tid = threadIdx.x;
     const int T = ws.totals[1];
     if (ws.err[0]) return;
     init_raydir<R, NT>(sm, tid);
-    const float inv_half_stride = 2.f / a.grid.stride[0];
 
-    // The warp runs one chunk ahead of itself: it draws the next chunk before the sweep and fetches that
-    // chunk's descriptor and contour into registers after it, so the loads are in flight during the
-    // settlement and land in shared memory at the top of the loop.
+    // Blocks draw chunks from a global counter (k_gt_setup zeroes it): chunk costs vary a lot with the GT's
+    // shape, and a static split leaves blocks idle at the end.  Warp 0 runs one chunk ahead: it draws the
+    // next chunk before the sweep and fetches that chunk's descriptor and contour into registers after it,
+    // so the loads are in flight during the settlement and land in shared memory at the next barrier.
     int n_work = T, n_bg = -1, n_desc = 0;
     float n_contour[CW];
-    auto fetch_next = [&](int drawn) {          // all lanes; `drawn` valid in lane 0
+    auto fetch_next = [&](int drawn) {          // warp 0, all lanes; `drawn` valid in lane 0
         const int unit = __shfl_sync(0xffffffffu, drawn, 0);
         n_work = T;
         n_bg = -1;
@@ -275,18 +293,24 @@ __global__ void __launch_bounds__(32) k_cand_arcs(const __grid_constant__ Assign
             n_desc = T;
         }
     };
-    {
+    if (tid < 32) {
         int drawn = 0;
         if (tid == 0) drawn = atomicAdd(&ws.totals[2], 1);
         fetch_next(drawn);
     }
     for (;;) {
-        __syncwarp();   // the previous chunk's contour and descriptor are no longer read
-        float l2max = 0.f;
-        bool lattice = false;
-        if (n_bg >= 0) lattice = arc_stage_contour<R, NT, CW>(sm, n_contour, tid, inv_half_stride, &l2max);
-        if (tid < 4 + 4 * YCR_MAX_LEVELS) s_desc[tid] = n_desc;
-        __syncwarp();
+        __syncthreads();   // both warps are done with the previous chunk's contour and descriptor
+        if (tid < 32) {
+            if (n_bg >= 0) {
+                float* dst = reinterpret_cast<float*>(sm.contour);
+#pragma unroll
+                for (int k = 0; k < CW; ++k)
+                    if (k * 32 + tid < 2 * YCR_C) dst[k * 32 + tid] = n_contour[k];
+            }
+            if (tid < 4 + 4 * YCR_MAX_LEVELS) s_desc[tid] = n_desc;
+            if (tid < 6) s_ctl[tid] = (tid < 2) ? -1 : 0;
+        }
+        __syncthreads();
         const int work = s_desc[2];
         if (work >= T) break;
         const int bg = s_desc[3];
@@ -313,18 +337,21 @@ __global__ void __launch_bounds__(32) k_cand_arcs(const __grid_constant__ Assign
             const int label = (int)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
             score = a.pred.cls[l][(int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
                                   (int64_t)label * a.pred.cls_sc[l]];
+            polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
         }
-        int nscan = 0;
-        const int nq = arc_chunk_targets<R, NT>(sm, a.ac, tid, active, ax, ay, 25.f * l2max, lattice, &nscan);
-        fetch_next(drawn);
-#if YA_STATS
-        if (tid == 0) {
-            atomicAdd(&g_ycr_stats[0], (unsigned long long)max(0, min(32, ncand - (work - s_desc[0]) * NT)));
+        if (tid < 32) fetch_next(drawn);
+        const int nq = polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        int nscan;
+        if constexpr (NT == 64 && K1_SHARE_QUEUES) nscan = polar_settle_queue_shared<R, NT>(sm, a.pc, tid, nq, s_ctl);
+        else nscan = polar_settle_queue<R, NT>(sm, a.pc, tid, nq);
+#if YCR_STATS   // measurement builds only (YCR_NVCC_FLAGS=-DYCR_STATS=1): three global atomics per warp and chunk
+        if ((tid & 31) == 0) {
+            atomicAdd(&g_ycr_stats[0], (unsigned long long)max(0, min(32, ncand - (work - s_desc[0]) * NT - (tid & ~31))));
             atomicAdd(&g_ycr_stats[1], (unsigned long long)nq);
             atomicAdd(&g_ycr_stats[2], (unsigned long long)nscan);
         }
 #else
-        (void)nq;
+        (void)nscan;
 #endif
         if (active) {
             const float rs = a.pred.ray_scale[ap.level];
@@ -657,33 +684,27 @@ struct PosArgs {
     int with_loss; float box_gain;
 };
 
-template <int R>
-__global__ void __launch_bounds__(32) k_positive_targets(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
-                                                         const PosArgs pa) {
+template <int R, int NT>
+__global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+                                                          const PosArgs pa) {
     pdl_enter();
-    constexpr int NT = 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ArcSmem<R, NT>& sm = *reinterpret_cast<ArcSmem<R, NT>*>(smem_raw);
-    constexpr int CW = (2 * YCR_C + 31) / 32;
+    PolarSmem<R, NT>& sm = *reinterpret_cast<PolarSmem<R, NT>*>(smem_raw);
     const int bg = blockIdx.x, tid = threadIdx.x;
     const int cnt = ws.gt_row_cnt[bg];
     if (cnt == 0) return;
     const int b = bg / a.gt.G;
     init_raydir<R, NT>(sm, tid);
-    float l2max = 0.f;
-    bool lattice;
     {
         const float* cp = a.gt.coor + (int64_t)bg * a.gt.coor_stride;
-        float reg[CW];
-#pragma unroll
-        for (int k = 0; k < CW; ++k)
-            if (k * 32 + tid < 2 * YCR_C) reg[k] = cp[k * 32 + tid];
-        lattice = arc_stage_contour<R, NT, CW>(sm, reg, tid, 2.f / a.grid.stride[0], &l2max);
+        float* dst = reinterpret_cast<float*>(sm.contour);
+        for (int k = tid; k < 2 * YCR_C; k += NT) dst[k] = cp[k];
     }
     const int row0 = ws.gt_row_start[bg];
     const int base = pa.img_base[b];
     for (int r0 = 0; r0 < cnt; r0 += NT) {
-        __syncwarp();
+        __syncthreads();
+        __syncthreads();
         const int r = r0 + tid;
         const bool active = r < cnt;
         const int row = row0 + r;
@@ -693,8 +714,10 @@ __global__ void __launch_bounds__(32) k_positive_targets(const __grid_constant__
             ap = anchor_pos(a.grid, ws.pos_anchor[(int64_t)b * ws.pos_cap + row]);
             ax = anchor_coord(ap.ix, a.grid.stride[ap.level]);
             ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
+            polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
         }
-        arc_chunk_targets<R, NT>(sm, a.ac, tid, active, ax, ay, 25.f * l2max, lattice, nullptr);
+        const int nq = polar_settle_own<R, NT>(sm, a.pc, tid, active, ax, ay);
+        polar_settle_queue<R, NT>(sm, a.pc, tid, nq);
         if (!active) continue;
         const int grow = base + row;
         float tmin = 3.4e38f, tmax = 0.f;
@@ -914,15 +937,16 @@ size_t assign_ws_layout(AssignWs* ws, void* base, const GridDev& grid, int B, in
 
 template <int R>
 static int launch_k1(const AssignArgs& a, const AssignWs& ws, cudaStream_t st) {
-    const size_t smem = sizeof(ArcSmem<R, 32>);
-    YCR_CUDA_CHECK(cudaFuncSetAttribute(k_cand_arcs<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr int NT1 = K1Nt<R>::value;
+    const size_t smem = sizeof(PolarSmem<R, NT1>);
+    YCR_CUDA_CHECK(cudaFuncSetAttribute(k_cand_overlaps<R, NT1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    YCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cand_arcs<R>, 32, smem));
+    YCR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cand_overlaps<R, NT1>, NT1, smem));
     if (per_sm < 1) per_sm = 1;
     int dev = 0, sms = YCR_NUM_SMS;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    { YcrProfScope ps(YCR_T_CAND, st); YCR_CUDA_CHECK(ycr_launch(k_cand_arcs<R>, dim3(sms * per_sm), dim3(32), smem, st, a, ws)); }
+    { YcrProfScope ps(YCR_T_CAND, st); YCR_CUDA_CHECK(ycr_launch(k_cand_overlaps<R, NT1>, dim3(sms * per_sm), dim3(NT1), smem, st, a, ws)); }
     YCR_LAUNCH_CHECK();
     return YCR_OK;
 }
@@ -970,13 +994,13 @@ int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_d
         return YCR_OK;
     }
     if (a.cfg.rays == 36) {
-        const size_t smem = sizeof(ArcSmem<36, 32>);
-        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        YCR_CUDA_CHECK(ycr_launch(k_positive_targets<36>, dim3(BG), dim3(32), smem, st, a, ws, pa));
+        const size_t smem = sizeof(PolarSmem<36, K4_NT>);
+        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<36, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YCR_CUDA_CHECK(ycr_launch(k_positive_targets<36, K4_NT>, dim3(BG), dim3(K4_NT), smem, st, a, ws, pa));
     } else {
-        const size_t smem = sizeof(ArcSmem<72, 32>);
-        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        YCR_CUDA_CHECK(ycr_launch(k_positive_targets<72>, dim3(BG), dim3(32), smem, st, a, ws, pa));
+        const size_t smem = sizeof(PolarSmem<72, K4_NT>);
+        YCR_CUDA_CHECK(cudaFuncSetAttribute(k_positive_targets<72, K4_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        YCR_CUDA_CHECK(ycr_launch(k_positive_targets<72, K4_NT>, dim3(BG), dim3(K4_NT), smem, st, a, ws, pa));
     }
     YCR_LAUNCH_CHECK();
     return YCR_OK;

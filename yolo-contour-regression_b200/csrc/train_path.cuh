@@ -1,7 +1,7 @@
 // Internal interface between the C-ABI wrappers (api.cu) and the training-path kernels.
 #pragma once
 #include "common.cuh"
-#include "polar_arcs.cuh"
+#include "polar_core.cuh"
 
 // Everything the assignment stage leaves in the workspace.
 struct AssignWs {
@@ -52,7 +52,7 @@ struct AssignArgs {
     ycr_pred_view_t pred;
     ycr_gt_t gt;
     ycr_assign_cfg_t cfg;
-    ArcConst ac;
+    PolarConst pc;
 };
 
 int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cudaStream_t st);
