@@ -209,7 +209,7 @@ int ycr_decode_best(const ycr_grid_t* grid, const float* const* feats, int B, in
 typedef struct {
     float conf_thres, iou_thres;
     int agnostic, multi_label;
-    int max_det, nc, max_nms;
+    int max_det, nc, max_nms; /* 1 <= max_det <= 1024 (YCR_E_ARG beyond: the kept list lives in shared memory) */
     float max_wh;
     const int* classes; int n_classes; /* optional device list of class ids to keep, utils/ops.py:390 */
     int compact_rows;   /* 0: image b's rows start at out_rows[b*max_det]; 1: rows of all images back to back

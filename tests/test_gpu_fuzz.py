@@ -36,7 +36,7 @@ def test_random_config_matches_oracle(case):
     cfg = synth.PathConfig("fz", B, G, S, rays=R, nc=nc)
     crit = v8SegmentationLoss(nc=nc, nm=R, strides=cfg.strides, device=dev)
     compared = tried = 0
-    for seed in range(seed0 * 10, seed0 * 10 + 4):
+    for seed in range(seed0 * 10, seed0 * 10 + 10):
         batch = synth.make_gts(cfg, seed, ragged=ragged)
         feats = synth.make_feats_near_gt(cfg, seed, batch) if seed % 2 else synth.make_feats(cfg, seed)
         ref = po.seg_loss(feats, batch, cfg.strides, nc, R)
@@ -53,4 +53,4 @@ def test_random_config_matches_oracle(case):
             assert float((f.grad.cpu() - r).abs().max()) <= TOL * max(float(r.abs().max()), 1e-30), (case, seed)
         if compared == 2:
             break
-    assert compared >= 1 or tried >= 4
+    assert compared >= 1, f"none of {tried} draws was tie-free: nothing was compared"

@@ -148,12 +148,13 @@ def require_cuda(*tensors):
 
 
 class Workspace:
-    """Grow-only device scratch buffer, one per (device, purpose)."""
+    """Grow-only device scratch buffer, one per (purpose, device, stream): calls on different streams must not
+    share scratch memory, calls on one stream are ordered."""
     _bufs: dict = {}
 
     @classmethod
     def get(cls, key, nbytes, device):
-        k = (key, str(device))
+        k = (key, str(device), torch.cuda.current_stream(device).cuda_stream)
         buf = cls._bufs.get(k)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)

@@ -759,6 +759,33 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
     }
 }
 
+// Ray target of (anchor, ray) straight from the contour in global memory, one thread, exact scan: only for a
+// positive that lies outside its GT's box.  That happens when an anchor picked by several GTs has overlap 0 with
+// all of them (predictions of +inf): argmax over all-zero overlaps is GT 0 (utils/tal.py:231), whatever its box,
+// and the reference computes real geometry for every mask_pos entry (utils/tal.py:1172-1193).
+template <int R>
+__device__ __noinline__ float ray_target_global(const float* __restrict__ coor, const PolarConst& pc, float ax, float ay, int ray) {
+    const double ang = (double)(ray * (360 / R)) * (3.14159265358979323846 / 180.0);
+    const float cr = (float)cos(ang), sr = (float)sin(ang);
+    uint4 K = make_uint4(YCR_EMPTY, YCR_EMPTY, YCR_EMPTY, YCR_EMPTY);
+    for (int j = 0; j < YCR_C; ++j) {
+        float vx = coor[2 * j] - ax;
+        const float vy = coor[2 * j + 1] - ay;
+        if (vx == 0.f && vy == 0.f) vx = 1.f;
+        insert4(K.x, K.y, K.z, K.w, pack_pseudo(pseudo_angle(fabsf(fmaf(vy, cr, -vx * sr)), fmaf(vx, cr, vy * sr)), j));
+    }
+    if ((K.x >> 9) > pc.q2_gate) return YCR_FLOOR;
+    const uint32_t e[4] = {K.x, K.y, K.z, K.w};
+    float m = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int j = (int)(e[q] & 511u);
+        const float vx = coor[2 * j] - ax, vy = coor[2 * j + 1] - ay;
+        m = fmaxf(m, fmaf(vx, vx, vy * vy));
+    }
+    return fmaxf(sqrtf(m), YCR_FLOOR);
+}
+
 // K4 (gather form): when K1 kept the ray targets of every candidate, a positive's targets are just read
 // back - one warp per positive, lanes over the rays; same outputs as k_positive_targets.
 template <int R>
@@ -799,7 +826,9 @@ __global__ void __launch_bounds__(256) k_positive_gather(const __grid_constant__
     for (int k = 0; k < NR; ++k) {
         const int i = lane + 32 * k;
         if (i < R) {
-            t[k] = tp ? tp[i * NT1] : YCR_FLOOR;
+            t[k] = tp ? tp[i * NT1]
+                      : ray_target_global<R>(a.gt.coor + (int64_t)bg * a.gt.coor_stride, a.pc,
+                                             anchor_coord(ap.ix, a.grid.stride[l]), anchor_coord(ap.iy, a.grid.stride[l]), i);
             tmin = fminf(tmin, t[k]);
             tmax = fmaxf(tmax, t[k]);
             smin += fmaxf(fminf(p[k], t[k]), YCR_FLOOR);

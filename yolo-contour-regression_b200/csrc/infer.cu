@@ -577,6 +577,11 @@ size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_
 
 int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (cfg->max_det < 1 || cfg->max_det > NMS_MAX_KEEP) {
+        ycr_set_error("max_det = %d: the suppression kernel keeps at most %d boxes per image in shared memory", cfg->max_det,
+                      NMS_MAX_KEEP);
+        return YCR_E_ARG;
+    }
     NmsWs ws;
     const size_t need = nms_ws_layout(&ws, workspace, B, A, cfg);
     if (need > workspace_bytes) { ycr_set_error("nms workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }

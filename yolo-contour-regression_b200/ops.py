@@ -28,14 +28,15 @@ def non_max_suppression(
     Boxes are already xyxy (the polar variant does not convert).  One filter kernel, one per-image sort
     kernel and one per-image suppression+gather kernel replace the per-image Python loop; the only host
     synchronisation is the read of the B kept-counts that the list-of-tensors return type requires.
-    `max_time_img` is accepted and ignored (no wall-clock bail-out).  Apriori `labels` (save_hybrid
-    autolabelling, utils/ops.py:368-374) are not supported."""
+    `max_time_img` is accepted and ignored (no wall-clock bail-out).  `max_det` is limited to 1024 (ValueError
+    beyond).  Apriori `labels` (save_hybrid autolabelling, utils/ops.py:368-374): the label rows of image i
+    ([class, x1, y1, x2, y2] each) join that image's candidates with score 1.0 for their class and zero masks,
+    as the reference intends (its own `v` is one column too wide for the polar layout, utils/ops.py:370, and
+    raises in torch.cat)."""
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     if isinstance(prediction, (list, tuple)):
         prediction = prediction[0]
-    if labels and any(len(lb) for lb in labels):
-        raise NotImplementedError("apriori labels (save_hybrid) are outside the B200 hot path")
     L.require_cuda(prediction)
     dev = prediction.device
     pred = prediction if (prediction.dtype == torch.float32 and prediction.is_contiguous()) \
@@ -43,6 +44,20 @@ def non_max_suppression(
     B, CH, A = pred.shape
     nc = nc or (CH - 4)
     nm = CH - nc - 4
+    if max_det > 1024:
+        raise ValueError(f"max_det={max_det}: at most 1024 detections per image are supported")
+    if labels and any(len(lb) for lb in labels):
+        # apriori labels become extra candidate columns: box, a one-hot class score of 1.0, zero masks
+        n_extra = max(len(lb) for lb in labels)
+        extra = torch.zeros(B, CH, n_extra, device=dev, dtype=torch.float32)
+        for xi, lb in enumerate(labels):
+            if len(lb):
+                lb = torch.as_tensor(lb, dtype=torch.float32, device=dev).reshape(-1, 5)
+                k = torch.arange(lb.shape[0], device=dev)
+                extra[xi, :4, :lb.shape[0]] = lb[:, 1:5].t()
+                extra[xi, 4 + lb[:, 0].long(), k] = 1.0
+        pred = torch.cat((pred, extra), 2).contiguous()
+        A = pred.shape[2]
     cfg = L.NmsCfg()
     cfg.conf_thres, cfg.iou_thres = float(conf_thres), float(iou_thres)
     cfg.agnostic, cfg.multi_label = int(bool(agnostic)), int(bool(multi_label) and nc > 1)
