@@ -227,6 +227,21 @@ size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* 
 int ycr_nms(const float* prediction, int B, int channels, int A, const ycr_nms_cfg_t* cfg, float* out_rows,
             int* out_counts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- validation: contour -> mask rasterisation and mask IoU ------------------------------ */
+
+/* Replaces the fill loop ops.process_mask has commented out (utils/ops.py:768-825, :794-809): rows are NMS output
+ * rows [box4 | conf | cls | x_0.. | y_0.. | valid_0..] (row_stride floats apart, 6+3R used); for each of the n
+ * detections the valid contour points are truncated to int32 and filled as cv2.fillPoly does (boundary lines +
+ * even-odd scan lines, 16.16 fixed point) into masks (n, H, W) uint8, values 0/1. */
+int ycr_rasterize_contours(const float* rows, int64_t row_stride, int n, int R, int H, int W, uint8_t* masks, void* stream);
+
+/* Replaces metrics.mask_iou (utils/metrics.py:133-155): mask1 (N, n) and mask2 (M, n), uint8 (dtype 0) or
+ * float32 (dtype 1), non-zero = set -> iou (N, M) = inter / (area1 + area2 - inter + eps) in fp32.  Both sets are
+ * bit-packed into the workspace, intersections are popcounts. */
+size_t ycr_mask_iou_workspace_bytes(int N, int M, int64_t n);
+int ycr_mask_iou(const void* mask1, int dtype1, const void* mask2, int dtype2, int N, int M, int64_t n, float eps, float* iou,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -525,3 +525,125 @@ def resample_segments(segments, n: int = 360):
         xp = np.arange(len(s))
         out.append(np.concatenate([np.interp(x, xp, s[:, i]) for i in range(2)], dtype=np.float32).reshape(2, -1).T)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# contour -> mask rasterisation
+# --------------------------------------------------------------------------------------------
+def _clip_line(w, h, p1, p2):
+    """cv2.clipLine (OpenCV 4.x drawing.cpp): Cohen-Sutherland with double arithmetic truncated to integers."""
+    x1, y1 = p1
+    x2, y2 = p2
+    right, bottom = w - 1, h - 1
+    c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8
+    c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8
+    if (c1 & c2) == 0 and (c1 | c2) != 0:
+        if c1 & 12:
+            a = 0 if c1 < 8 else bottom
+            x1 += int(float(a - y1) * (x2 - x1) / (y2 - y1))
+            y1 = a
+            c1 = (x1 < 0) + (x1 > right) * 2
+        if c2 & 12:
+            a = 0 if c2 < 8 else bottom
+            x2 += int(float(a - y2) * (x2 - x1) / (y2 - y1))
+            y2 = a
+            c2 = (x2 < 0) + (x2 > right) * 2
+        if (c1 & c2) == 0 and (c1 | c2) != 0:
+            if c1:
+                a = 0 if c1 == 1 else right
+                y1 += int(float(a - x1) * (y2 - y1) / (x2 - x1))
+                x1 = a
+                c1 = 0
+            if c2:
+                a = 0 if c2 == 1 else right
+                y2 += int(float(a - x2) * (y2 - y1) / (x2 - x1))
+                x2 = a
+                c2 = 0
+    return (c1 | c2) == 0, (x1, y1), (x2, y2)
+
+
+def _draw_line(img, p0, p1):
+    """cv2.line(..., thickness 1, 8-connected): clipLine, then LineIterator left to right."""
+    h, w = img.shape
+    ok, p0, p1 = _clip_line(w, h, p0, p1)
+    if not ok:
+        return
+    (x0, y0), (x1, y1) = p0, p1
+    dx, dy = x1 - x0, y1 - y0
+    if dx < 0:
+        x0, y0, dx, dy = x1, y1, -dx, -dy
+    sy = 1 if dy >= 0 else -1
+    dy = abs(dy)
+    steep = dy > dx
+    a, b = (dy, dx) if steep else (dx, dy)
+    err, x, y = a - 2 * b, x0, y0
+    for _ in range(a + 1):
+        if 0 <= x < w and 0 <= y < h:
+            img[y, x] = 1
+        m = err < 0
+        err += -2 * b + (2 * a if m else 0)
+        if steep:
+            y += sy
+            x += 1 if m else 0
+        else:
+            x += 1
+            y += sy if m else 0
+
+
+def fill_poly(points, h, w):
+    """cv2.fillPoly(img, [points], color) for one integer polygon (the step utils/ops.py:794-809 has commented out):
+    boundary lines plus even-odd scan-line fill in 16.16 fixed point (OpenCV drawing.cpp CollectPolyEdges /
+    FillEdgeCollection): an edge covers scan lines y0 <= y < y1 with x = x0 + (y - y0) * dx, dx the truncated
+    quotient; between the sorted crossings of a pair the pixels ceil(xa) .. floor(xb) are set.  -> (h,w) uint8 0/1.
+    Pinned against cv2.fillPoly in tests/test_oracle_golden.py."""
+    ONE = 1 << 16
+    img = np.zeros((h, w), np.uint8)
+    pts = [(int(p[0]), int(p[1])) for p in points]
+    n = len(pts)
+    if n == 0:
+        return img
+    edges = []
+    for i in range(n):
+        p0, p1 = pts[i - 1], pts[i]
+        _draw_line(img, p0, p1)
+        if p0[1] == p1[1]:
+            continue
+        if p0[1] < p1[1]:
+            y0, y1, x = p0[1], p1[1], p0[0] * ONE
+        else:
+            y0, y1, x = p1[1], p0[1], p1[0] * ONE
+        num, den = (p1[0] - p0[0]) * ONE, p1[1] - p0[1]
+        q = abs(num) // abs(den)
+        edges.append((y0, y1, x, q if (num >= 0) == (den > 0) else -q))
+    if n < 3 and not edges:
+        return img
+    for y in range(0, h):
+        xs = sorted(x + (y - y0) * d for (y0, y1, x, d) in edges if y0 <= y < y1)
+        for k in range(0, len(xs) - 1, 2):
+            x1, x2 = (xs[k] + ONE - 1) >> 16, xs[k + 1] >> 16
+            if x1 < w and x2 >= 0:
+                x1, x2 = max(x1, 0), min(x2, w - 1)
+                if x1 <= x2:
+                    img[y, x1:x2 + 1] = 1
+    return img
+
+
+def contour_masks(rows, R, h, w):
+    """The intended ops.process_mask of the polar fork (utils/ops.py:768-825 with the commented loop restored):
+    rows (n, 6+3R) NMS output; per detection the valid contour points, truncated to int32, filled -> (n,h,w) uint8."""
+    rows = np.asarray(rows, np.float32)
+    out = np.zeros((rows.shape[0], h, w), np.uint8)
+    for i, r in enumerate(rows):
+        xx, yy, ok = r[6:6 + R], r[6 + R:6 + 2 * R], r[6 + 2 * R:6 + 3 * R] != 0
+        pts = list(zip(xx[ok].astype(np.int32).tolist(), yy[ok].astype(np.int32).tolist()))
+        out[i] = fill_poly(pts, h, w)
+    return out
+
+
+def mask_iou(m1, m2, eps=1e-7):
+    """utils/metrics.py:133-155 mask_iou: (N,n) x (M,n) 0/1 masks -> (N,M) IoU in fp32."""
+    a = torch.as_tensor(m1).float()
+    b = torch.as_tensor(m2).float()
+    inter = torch.matmul(a, b.t()).clamp(0)
+    union = (a.sum(1)[:, None] + b.sum(1)[None]) - inter
+    return inter / (union + eps)

@@ -85,6 +85,10 @@ EXPORTS = {
                              C.c_void_p]),
     "ycr_decode_best": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "ycr_rasterize_contours": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "ycr_mask_iou_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
+    "ycr_mask_iou": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_void_p,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "ycr_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg)]),
     "ycr_nms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg), C.c_void_p, C.c_void_p,
                           C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -50,6 +50,11 @@ size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg);
 int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
                void* workspace, size_t workspace_bytes, cudaStream_t st);
 
+int launch_rasterize(const float* rows, int64_t row_stride, int n, int R, int H, int W, uint8_t* masks, cudaStream_t st);
+size_t mask_iou_workspace_bytes(int N, int M, int64_t n);
+int launch_mask_iou(const void* m1, int dt1, const void* m2, int dt2, int N, int M, int64_t n, float eps, float* iou,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 static int check_common(const ycr_grid_t* grid, const ycr_assign_cfg_t* cfg, int B, int G) {
     if (!grid || !cfg) { ycr_set_error("null grid/cfg"); return YCR_E_ARG; }
     if (grid->n_levels < 1 || grid->n_levels > YCR_MAX_LEVELS) { ycr_set_error("n_levels %d out of range", grid->n_levels); return YCR_E_ARG; }
@@ -270,6 +275,26 @@ int ycr_nms(const float* prediction, int B, int channels, int A, const ycr_nms_c
     if (cfg->nc < 1 || 4 + cfg->nc > channels) { ycr_set_error("bad nc %d for %d channels", cfg->nc, channels); return YCR_E_ARG; }
     return launch_nms(prediction, B, channels, A, cfg, out_rows, out_counts, workspace, workspace_bytes,
                       reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ycr_rasterize_contours(const float* rows, int64_t row_stride, int n, int R, int H, int W, uint8_t* masks, void* stream) {
+    if (n < 0 || R < 1 || R > 72 || H < 1 || W < 1 || row_stride < 6 + 3 * R || (n > 0 && (!rows || !masks))) {
+        ycr_set_error("bad rasterize arguments");
+        return YCR_E_ARG;
+    }
+    return launch_rasterize(rows, row_stride, n, R, H, W, masks, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ycr_mask_iou_workspace_bytes(int N, int M, int64_t n) { return (N < 0 || M < 0 || n < 1) ? 0 : mask_iou_workspace_bytes(N, M, n); }
+
+int ycr_mask_iou(const void* mask1, int dtype1, const void* mask2, int dtype2, int N, int M, int64_t n, float eps, float* iou,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+    if (N < 0 || M < 0 || n < 1 || ((N > 0 && M > 0) && (!mask1 || !mask2 || !iou || !workspace))) {
+        ycr_set_error("bad mask_iou arguments");
+        return YCR_E_ARG;
+    }
+    return launch_mask_iou(mask1, dtype1, mask2, dtype2, N, M, n, eps, iou, workspace, workspace_bytes,
+                           reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -15,6 +15,9 @@ PATCHES = (
     ("ultralytics.utils.loss", "TaskAlignedAssigner", "tal", "TaskAlignedAssigner"),
     ("ultralytics.nn.tasks", "v8SegmentationLoss", "loss", "v8SegmentationLoss"),
     ("ultralytics.utils.ops", "non_max_suppression", "ops", "non_max_suppression"),
+    ("ultralytics.utils.ops", "process_mask", "ops", "process_mask"),
+    ("ultralytics.utils.metrics", "mask_iou", "ops", "mask_iou"),
+    ("ultralytics.models.yolo.segment.val", "mask_iou", "ops", "mask_iou"),
     ("ultralytics.nn.modules.head", "Segment", "head", "Segment"),
     ("ultralytics.nn.modules", "Segment", "head", "Segment"),
     ("ultralytics.nn.tasks", "Segment", "head", "Segment"),

@@ -110,3 +110,64 @@ def resample_segments(segments, n=1000, device=None):
     rc = L.lib().ycr_resample_segments(pts.data_ptr(), offs_d.data_ptr(), len(ts), int(n), out.data_ptr(), L.stream_ptr(dev))
     L.check(rc, "ycr_resample_segments")
     return list(out.unbind(0))
+
+
+def process_mask(protos, masks_in, bboxes, shape, upsample=False):
+    """utils/ops.py:768-825 (polar variant) with the fill loop it has commented out (:794-809) done on the device:
+    `masks_in` (n, 3R) are the mask columns of NMS rows [x_0.. | y_0.. | valid_0..]; per detection the valid contour
+    points, truncated to int32, are filled as cv2.fillPoly does -> (n, h, w) uint8 masks with values 0/1
+    (float32 when `upsample`, the predictor's call, which feeds them to Results).  `protos` and `bboxes` are
+    accepted and unused, as in the reference."""
+    L.require_cuda(masks_in)
+    n, pn = masks_in.shape
+    R = pn // 3
+    h, w = int(shape[0]), int(shape[1])
+    dev = masks_in.device
+    rows = torch.empty(n, 6 + 3 * R, device=dev, dtype=torch.float32)
+    rows[:, 6:] = masks_in.float()
+    masks = torch.empty(n, h, w, device=dev, dtype=torch.uint8)
+    rc = L.lib().ycr_rasterize_contours(rows.data_ptr(), rows.stride(0), n, R, h, w, masks.data_ptr(), L.stream_ptr(dev))
+    L.check(rc, "ycr_rasterize_contours")
+    return masks.float() if upsample else masks
+
+
+def rasterize_rows(rows, R, shape):
+    """Same, straight from NMS rows (n, 6+3R) - no copy of the mask columns."""
+    L.require_cuda(rows)
+    rows = rows if (rows.dtype == torch.float32 and rows.stride(1) == 1) else rows.float().contiguous()
+    n = rows.shape[0]
+    h, w = int(shape[0]), int(shape[1])
+    masks = torch.empty(n, h, w, device=rows.device, dtype=torch.uint8)
+    rc = L.lib().ycr_rasterize_contours(rows.data_ptr(), rows.stride(0), n, int(R), h, w, masks.data_ptr(),
+                                        L.stream_ptr(rows.device))
+    L.check(rc, "ycr_rasterize_contours")
+    return masks
+
+
+def mask_iou(mask1, mask2, eps=1e-7):
+    """utils/metrics.py:133-155: mask1 (N, n) ground-truth masks, mask2 (M, n) predicted masks (uint8 or float,
+    non-zero = set) -> (N, M) IoU.  Both sets are bit-packed and intersected with popcounts instead of the
+    reference's (N, n) x (n, M) float matmul."""
+    L.require_cuda(mask1, mask2)
+    dev = mask1.device
+
+    def prep(m):
+        if m.dtype == torch.bool:
+            m = m.to(torch.uint8)
+        if m.dtype not in (torch.uint8, torch.float32):
+            m = m.float()
+        return m.contiguous(), (0 if m.dtype == torch.uint8 else 1)
+    a, da = prep(mask1)
+    b, db = prep(mask2)
+    N, n = a.shape
+    M = b.shape[0]
+    out = torch.zeros(N, M, device=dev, dtype=torch.float32)
+    if N == 0 or M == 0:
+        return out
+    lib = L.lib()
+    nbytes = lib.ycr_mask_iou_workspace_bytes(N, M, n)
+    ws = L.Workspace.get("mask_iou", nbytes, dev)
+    rc = lib.ycr_mask_iou(a.data_ptr(), da, b.data_ptr(), db, N, M, n, float(eps), out.data_ptr(), ws.data_ptr(),
+                          ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "ycr_mask_iou")
+    return out
