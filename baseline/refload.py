@@ -60,3 +60,27 @@ def load():
 def model_yaml() -> str:
     """The polar segmentation model definition of the reference's repository root (nm=36, nc=10)."""
     return os.path.join(REF_DIR, "yolov8-seg.yaml")
+
+
+def reference_criterion(nc, rays, strides, box=7.5, cls=0.5):
+    """The reference's v8SegmentationLoss (utils/loss.py:772) on the CPU, built on a stub of the two objects its
+    constructor reads (`model.args`, `model.model[-1]`), so the loss path can be driven without the conv backbone."""
+    from types import SimpleNamespace
+    import torch
+    load()
+    import ultralytics.utils.loss as rloss
+
+    class _Head(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.nc, self.nm, self.no, self.reg_max = nc, rays, nc + rays, 16
+            self.stride = torch.tensor(strides, dtype=torch.float32)
+            self.w = torch.nn.Parameter(torch.zeros(1))
+
+    class _Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = torch.nn.ModuleList([_Head()])
+            self.args = SimpleNamespace(box=box, cls=cls, dfl=1.5, overlap_mask=True)
+
+    return rloss.v8SegmentationLoss(_Model())

@@ -15,8 +15,9 @@ batch, as the reference's DDP does; the path has no data-path collective, SURVEY
   infer   decode + NMS images/s on config C3 (batch 256 @640, conf .25 / IoU .7), same method
   cpu_baseline   the oracle port (torch-CPU restatement of the reference) on a bounded sample
 
-`--impl reference` times that CPU restatement alone on the host cores (the reference itself is Python
-under /root/reference and cannot travel to the GPU box)."""
+`--impl reference` times the reference's own v8SegmentationLoss (installed into the git-ignored baseline/_ref by
+baseline/install_reference.py, so it travels to the GPU box) on the host cores, on the first images of the same
+batch; the oracle port stands in when baseline/_ref is absent or the workload has 72 rays."""
 import argparse
 import ctypes as C
 import json
@@ -98,20 +99,43 @@ def dist_env():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, bounded sample
+# CPU arm: the reference itself (baseline/_ref, installed by baseline/install_reference.py) when it travelled with
+# the repo, else the oracle port; bounded sample of the same workload, same input generators as the GPU arm
 # ------------------------------------------------------------------------------------------------
-def cpu_train_sample(cfg, n_images, repeats, seed=101):
+def bench_inputs(cfg, seed, n_images=None):
+    """Synthetic inputs of one rank: the batch dict and the head feature maps (random head outputs,
+    16 distinct images tiled to the batch - both arms use this generator)."""
     from ycr_b200 import synth
-    from oracle import polar_oracle as po
-    sub = synth.PathConfig("cpu", n_images, cfg.gts, cfg.imgsz, rays=cfg.rays, nc=cfg.nc)
+    B = cfg.batch if n_images is None else n_images
+    sub = synth.PathConfig("gen", B, cfg.gts, cfg.imgsz, rays=cfg.rays, nc=cfg.nc)
     batch = synth.make_gts(sub, seed)
-    feats = synth.make_feats_near_gt(sub, seed, batch)
+    gen_cfg = synth.PathConfig("gen", min(B, 16), cfg.gts, cfg.imgsz, rays=cfg.rays, nc=cfg.nc)
+    reps = (B + gen_cfg.batch - 1) // gen_cfg.batch
+    small = synth.make_feats(gen_cfg, seed)
+    feats = [torch.cat([f.roll(k, 0) for k in range(reps)], 0)[:B].contiguous() for f in small]
+    return batch, feats
+
+
+def cpu_train_sample(cfg, n_images, repeats, seed=1000):
+    """-> (times, kind): fwd+bwd of v8SegmentationLoss on the first n_images of the GPU arm's rank-0 batch."""
+    from baseline import refload
+    batch, feats = bench_inputs(cfg, seed, n_images)
     times = []
+    if cfg.rays == 36 and refload.available():   # (the reference hard-codes 36 rays, utils/tal.py:1178)
+        crit = refload.reference_criterion(cfg.nc, cfg.rays, cfg.strides)
+        for _ in range(repeats):
+            fl = [f.clone().requires_grad_(True) for f in feats]
+            t0 = time.perf_counter()
+            total, items = crit((fl, 5, 2), batch)
+            total.backward()
+            times.append(time.perf_counter() - t0)
+        return times, "reference"
+    from oracle import polar_oracle as po
     for _ in range(repeats):
         t0 = time.perf_counter()
-        po.seg_loss(feats, batch, sub.strides, sub.nc, sub.rays, with_grad=True)
+        po.seg_loss(feats, batch, cfg.strides, cfg.nc, cfg.rays, with_grad=True)
         times.append(time.perf_counter() - t0)
-    return times
+    return times, "port"
 
 
 def run_reference(args):
@@ -123,23 +147,29 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n_img = args.cpu_images
-    times = cpu_train_sample(cfg, n_img, args.warmup + args.steps)
+    times, kind = cpu_train_sample(cfg, n_img, args.warmup + args.steps)
     timed = times[args.warmup:]
     ms = 1e3 * sum(timed) / len(timed)
     val = n_img / (ms / 1e3)
+    what = ("the reference's v8SegmentationLoss.__call__ fwd+bwd (baseline/_ref, torch CPU)" if kind == "reference"
+            else "oracle/polar_oracle.seg_loss fwd+bwd (port: baseline/_ref absent or rays != 36)")
     line = {
         "impl": "reference", "metric": "assign+polar-loss images/sec @640", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: v8SegmentationLoss fwd+bwd, batch {cfg.batch} @{cfg.imgsz}, "
-                               f"{cfg.gts} GTs/img, {cfg.rays} rays, nc={cfg.nc}",
-                   "sample": f"{n_img} images per step (bounded sample of the batch)"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_img} images/step x {args.steps} steps, oracle/polar_oracle.seg_loss fwd+bwd"},
+        "config": {"workload": workload_name(args.workload, cfg),
+                   "sample": f"{n_img} images per step (bounded sample of the GPU arm's rank-0 batch, same generators)"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": kind,
+                         "sample": f"{n_img} images/step x {args.steps} steps, {what}"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def workload_name(name, cfg):
+    return (f"{name}: v8SegmentationLoss.__call__ fwd+bwd from the head feature maps and the batch dict, "
+            f"batch {cfg.batch}/GPU @{cfg.imgsz}, {cfg.gts} GTs/img, {cfg.rays} rays, nc={cfg.nc}, A={cfg.anchors}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -196,21 +226,18 @@ def run_ours(args):
 
     # synthetic inputs (per rank: different seed, same shape)
     seed = 1000 + rank
-    batch = synth.make_gts(cfg, seed)
-    gen_cfg = synth.PathConfig("gen", min(B, 16), G, cfg.imgsz, rays=R, nc=nc)
-    reps = (B + gen_cfg.batch - 1) // gen_cfg.batch
-    small = synth.make_feats(gen_cfg, seed)
-    feats_h = [torch.cat([f.roll(k, 0) for k in range(reps)], 0)[:B].contiguous().pin_memory() for f in small]
+    batch, feats_cpu = bench_inputs(cfg, seed)
+    feats_h = [f.pin_memory() for f in feats_cpu]
     feats_d = [f.to(dev).requires_grad_(True) for f in feats_h]
     crit = v8SegmentationLoss(nc=nc, nm=R, strides=cfg.strides, device=dev)
-    crit._shapes = [tuple(f.shape[2:]) for f in feats_d]
-    packed, cap = crit.pack_targets(batch, B, (cfg.imgsz, cfg.imgsz))
     in_bytes = sum(f.numel() * 4 for f in feats_h)
 
     def step_resident():
+        # from the head feature maps (resident, requires_grad) + the batch dict (on the CPU,
+        # as the dataloader leaves it) to loss.backward() finished - GT packing is inside the region
         for f in feats_d:
             f.grad = None
-        total, items = crit.call_packed(feats_d, packed, cap)
+        total, items = crit((feats_d, 5, 2), batch)
         total.backward()
         return total
 
@@ -247,8 +274,10 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # host time to ISSUE a step (no sync inside)
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
@@ -351,8 +380,13 @@ def run_ours(args):
 
     # ---- reduce over ranks (max time) ----
     t = torch.tensor([ms_total, ms_e2e, ms_inf], device=dev, dtype=torch.float64)
+    per_rank = None
     if use_dist:
         import torch.distributed as dist
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank = {"ms_per_step": [float(g[0]) / args.steps for g in gathered],
+                    "e2e_ms_per_step": [float(g[1]) / e_steps for g in gathered]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, ms_inf = [float(x) for x in t.tolist()]
     if rank != 0:
@@ -362,10 +396,14 @@ def run_ours(args):
         return
 
     peak, peak_src = measured_peaks()
-    traffic = {}
+    # DRAM traffic of the dominant kernel: what an `ncu --set full` capture of this build measured (profiles/),
+    # never a number made up in the run; null when no capture of the current round exists
+    traffic, traffic_src = {}, None
     try:
         tf = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
-        traffic = json.load(open(os.path.join(ROOT, "profiles", tf[-1]))) if tf else {}
+        if tf:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", tf[-1])))
+            traffic_src = "profiles/" + tf[-1]
     except Exception:
         pass
     ms_step = ms_total / args.steps
@@ -384,30 +422,31 @@ def run_ours(args):
     inf_val = world * ib / (ms_inf / i_steps / 1e3)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cpu_times = cpu_train_sample(cfg, args.cpu_images, 3) if world == 1 else None
+    cpu_times, cpu_kind = cpu_train_sample(cfg, args.cpu_images, 3) if world == 1 else (None, None)
     cpu_val = (args.cpu_images / (sum(cpu_times[1:]) / len(cpu_times[1:]))) if cpu_times else None
     line = {
         "metric": "assign+polar-loss images/sec @640", "value": value, "unit": "images/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: v8SegmentationLoss fwd+bwd from head feats, batch {B}/GPU @{cfg.imgsz}, "
-                               f"{G} GTs/img, {R} rays, nc={nc}, A={A}",
+        "config": {"workload": workload_name(args.workload, cfg),
                    "l2": f"inputs per step {in_bytes / 1e6:.0f} MB + grads of the same size > 126 MB L2",
                    "parallelism": f"dp{world}, no data-path collective"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                      "frac": dom_gbs / peak, "traffic": traffic.get(dom) if args.workload == "C2" else None,
+                     "traffic_source": traffic_src if (args.workload == "C2" and traffic.get(dom)) else None,
                      "peak_source": peak_src,
                      "note": "algorithmic bytes of the whole path (SURVEY 8-d: %.2f MB/img) / avg duration of the "
                              "dominant kernel; see roofline_step and kernels_ms" % (bytes_img / 1e6)},
         "roofline_step": {"achieved": path_gbs, "peak": peak, "unit": "GB/s", "frac": path_gbs / peak,
                           "bytes_per_image": bytes_img},
         "kernels_ms": kern,
+        "host_issue_ms_per_step": host_issue_ms,
         "loss_stream_hbm_frac": (stream_bytes / (kern["loss_stream"] * 1e-3) / 1e9 / peak) if "loss_stream" in kern else None,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": in_bytes + gt_rows_bytes,
                 "d2h_bytes_per_step": 4, "steps": e_steps},
-        # per step: k_gt_rects, k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image, k_positive_gather,
-        # k_loss_stream_v4, k_loss_finalize, k_scale (torch's two gradient fills are not counted)
-        "gpu_launches": 9 * args.steps,
+        # per step: k_pack_index, k_pack_targets, k_gt_rects, k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image,
+        # k_positive_gather, k_loss_stream_v4, k_loss_finalize, k_scale (torch's fills and copies are not counted)
+        "gpu_launches": 11 * args.steps,
         "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
                   "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",
                   "ms_per_step": ms_inf / i_steps, "kernels_ms": ikern,
@@ -415,9 +454,12 @@ def run_ours(args):
         "clocks": clocks,
     }
     if cpu_val is not None:
-        line["cpu_baseline"] = {"value": cpu_val, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": f"{args.cpu_images} images of the same workload, fwd+bwd, "
-                                          f"1 warm-up + 2 timed (oracle/polar_oracle.seg_loss)"}
+        line["cpu_baseline"] = {"value": cpu_val, "unit": "images/s", "cores": cores, "kind": cpu_kind,
+                                "sample": f"the first {args.cpu_images} images of this batch, fwd+bwd, 1 warm-up + 2 timed ("
+                                          + ("the reference's v8SegmentationLoss, baseline/_ref" if cpu_kind == "reference"
+                                             else "oracle/polar_oracle.seg_loss") + ")"}
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     emit(line)
     if use_dist:
         import torch.distributed as dist

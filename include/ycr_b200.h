@@ -130,6 +130,10 @@ int ycr_debug_stats(unsigned long long* out_h, int reset);
  * the workspace without a device sync. */
 int64_t ycr_candidate_bound_h(const ycr_grid_t* grid, const float* boxes_h, int64_t row_stride, int n_rows);
 
+/* Same bound from the rows the dataloader holds: normalised (x, y, w, h) boxes, utils/loss.py:839. */
+int64_t ycr_candidate_bound_xywhn_h(const ycr_grid_t* grid, const float* xywhn_h, int64_t row_stride, int n_rows, float img_w,
+                                    float img_h);
+
 size_t ycr_assign_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg,
                                   int64_t cand_capacity);
 
@@ -173,6 +177,11 @@ int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* g
  * (normalised)], row_stride floats apart, any order of images — -> padded (B,G,725) in px. */
 int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,
                      float* out_packed, void* stream);
+
+/* Same with the two parts of a row in separate arrays - [image index, class, x, y, w, h] (head_stride floats apart) and
+ * the 720 contour values (seg_stride floats apart) - so that a caller can stage `batch['segments']` with one copy. */
+int ycr_pack_targets_split(const float* head, int64_t head_stride, const float* segments, int64_t seg_stride, int N, int B, int G,
+                           float img_w, float img_h, float* out_packed, void* stream);
 
 /* Contour resampling, replaces ops.resample_segments (utils/ops.py:676-693; n = 360 at
  * utils/instance.py:202): S open polygons stored back to back in pts (total,2); polygon s owns rows

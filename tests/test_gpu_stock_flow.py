@@ -30,6 +30,7 @@ def test_train_val_predict_flow_runs_on_rebound_kernels(ref):
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
     cfg, batch = fc.c1_batch(nc=10, seed=1)
 
     # ---- the untouched reference on the CPU ----
@@ -37,13 +38,12 @@ def test_train_val_predict_flow_runs_on_rebound_kernels(ref):
     m_ref = fc.build_model(nc=10)
     assert type(m_ref.model[-1]).__module__ == "ultralytics.nn.modules.head"
     state = {k: v.clone() for k, v in m_ref.state_dict().items()}
+    m_ref.eval()
+    with torch.no_grad():
+        allpred_ref = m_ref(batch["img"])[0]        # (before any training forward moves the BatchNorm statistics)
     m_ref.train()
     loss_ref, items_ref = m_ref(batch)
     loss_ref.backward()
-    gref = {n: p.grad.clone() for n, p in m_ref.named_parameters() if p.grad is not None}
-    m_ref.eval()
-    with torch.no_grad():
-        allpred_ref = m_ref(batch["img"])[0]
 
     # ---- the same flow after install() ----
     saved = {(m, a): getattr(sys.modules[m], a) for m, a, _, _ in install.PATCHES
@@ -60,18 +60,25 @@ def test_train_val_predict_flow_runs_on_rebound_kernels(ref):
         loss, items = m(gbatch)                                                 # BaseModel.forward -> loss -> criterion
         assert type(m.criterion).__module__.startswith("ycr_b200")
         loss.backward()
-        # the convolutions run in cuDNN here and in MKL there (fp32 both): the loss agrees to a few 1e-5
-        assert rel_err(items.cpu(), items_ref) < 2e-4, (items, items_ref)
-        assert rel_err(loss.detach().cpu(), loss_ref.detach()) < 2e-4
-        checked = 0
-        for n, p in m.named_parameters():
-            if n in gref and n.startswith(("model.22.cv2.2.2", "model.22.cv3.2.2", "model.22.cv2.0.2")):
-                g = p.grad.cpu()
-                assert float((g - gref[n]).abs().max()) <= 2e-3 * float(gref[n].abs().max()) + 1e-7, n
-                checked += 1
-        assert checked >= 4
+        # (1) the head outputs of the two builds agree (cuDNN here, MKL there, fp32 both) ...
+        with torch.no_grad():
+            feats = m._predict_once(gbatch["img"])[0]
+            m_ref.train()
+            feats_ref = m_ref._predict_once(batch["img"])[0]
+        for f, fr in zip(feats, feats_ref):
+            assert float((f.cpu() - fr).abs().max()) < 2e-3
+        # (2) ... and on the SAME head outputs the rebound criterion returns what the reference's criterion returns
+        # (checked below, once the reference's symbols are restored).
+        fg = [f.detach().clone().requires_grad_(True) for f in feats]
+        loss_g, items_g = m.criterion((fg, 5, 2), gbatch)
+        loss_g.backward()
+        same_feats = {"feats": [f.detach().cpu() for f in feats], "items": items_g.cpu(), "loss": loss_g.detach().cpu(),
+                      "grads": [f.grad.cpu() for f in fg]}
+        assert abs(float(loss) - float(loss_ref)) < 0.1 * float(loss_ref)        # same ball park end to end
+        assert sum(int(p.grad is not None and bool(torch.isfinite(p.grad).all())) for p in m.parameters()) > 100
 
         # ---- validator batch ----
+        m.load_state_dict(state, strict=True)       # the BatchNorm statistics of the untrained model again
         m.eval()
         with torch.no_grad():
             preds = m(gbatch["img"])
@@ -103,3 +110,16 @@ def test_train_val_predict_flow_runs_on_rebound_kernels(ref):
     finally:
         for (mod, a), val in saved.items():
             setattr(sys.modules[mod], a, val)
+
+    # ---- the reference's own criterion (symbols restored) on the head outputs the GPU model produced ----
+    # End to end the two losses differ by a few per cent at most: a freshly initialised head scores all anchors almost
+    # alike, so convolution noise of 1e-6 can reorder a per-GT top-10 - the reference's sensitivity, not the kernels'.
+    crit_ref = m_ref.init_criterion()
+    assert type(crit_ref).__module__ == "ultralytics.utils.loss"
+    fl = [f.clone().requires_grad_(True) for f in same_feats["feats"]]
+    loss_r, items_r = crit_ref((fl, 5, 2), batch)
+    loss_r.backward()
+    assert rel_err(same_feats["items"], items_r) < 1e-4, (same_feats["items"], items_r)
+    assert rel_err(same_feats["loss"], loss_r.detach()) < 1e-4
+    for a, b in zip(same_feats["grads"], fl):
+        assert float((a - b.grad).abs().max()) <= 1e-4 * float(b.grad.abs().max())

@@ -42,8 +42,8 @@ int launch_bbox_loss(const float* pred_dist, const float* pred_bboxes, const flo
                      int B, int A, int nc, int reg_max, int use_dfl, float* loss_out, float* grad_dist, float* grad_bboxes,
                      void* workspace, size_t workspace_bytes, cudaStream_t st);
 int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* scale, cudaStream_t st);
-int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
-                        cudaStream_t st);
+int launch_pack_targets(const float* head, int64_t hs, const float* seg, int64_t ss, int N, int B, int G, float img_w, float img_h,
+                        float* out, cudaStream_t st);
 int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, int2* best,
                   cudaStream_t st);
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg);
@@ -145,6 +145,23 @@ int64_t ycr_candidate_bound_h(const ycr_grid_t* grid, const float* boxes_h, int6
     return total;
 }
 
+int64_t ycr_candidate_bound_xywhn_h(const ycr_grid_t* grid, const float* xywhn_h, int64_t row_stride, int n_rows, float img_w,
+                                    float img_h) {
+    int64_t total = 0;
+    for (int r = 0; r < n_rows; ++r) {
+        const float* bx = xywhn_h + r * row_stride;
+        const double w = (double)bx[2] * img_w, h = (double)bx[3] * img_h;
+        if (!(w > 0) || !(h > 0)) continue;
+        for (int l = 0; l < grid->n_levels; ++l) {
+            int64_t cx = (int64_t)floor(w / grid->stride[l]) + 2, cy = (int64_t)floor(h / grid->stride[l]) + 2;
+            if (cx > grid->w[l]) cx = grid->w[l];
+            if (cy > grid->h[l]) cy = grid->h[l];
+            total += cx * cy;
+        }
+    }
+    return total;
+}
+
 size_t ycr_assign_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg, int64_t cand_capacity) {
     if (check_common(grid, cfg, B, G)) return 0;
     GridDev gd = make_grid_dev(grid);
@@ -222,7 +239,17 @@ int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int
     if (!out_packed || (N > 0 && !targets)) { ycr_set_error("null argument"); return YCR_E_ARG; }
     if (B < 1 || G < 0 || row_stride < 6 + 2 * YCR_C) { ycr_set_error("bad B/G/row_stride"); return YCR_E_ARG; }
     if (G == 0) return YCR_OK;
-    return launch_pack_targets(targets, row_stride, N, B, G, img_w, img_h, out_packed, reinterpret_cast<cudaStream_t>(stream));
+    return launch_pack_targets(targets, row_stride, targets + 6, row_stride, N, B, G, img_w, img_h, out_packed,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ycr_pack_targets_split(const float* head, int64_t head_stride, const float* segments, int64_t seg_stride, int N, int B, int G,
+                           float img_w, float img_h, float* out_packed, void* stream) {
+    if (!out_packed || (N > 0 && (!head || !segments))) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (B < 1 || G < 0 || head_stride < 6 || seg_stride < 2 * YCR_C) { ycr_set_error("bad B/G/strides"); return YCR_E_ARG; }
+    if (G == 0) return YCR_OK;
+    return launch_pack_targets(head, head_stride, segments, seg_stride, N, B, G, img_w, img_h, out_packed,
+                               reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ycr_resample_segments(const float* pts, const int* offsets, int S, int n_out, float* out, void* stream) {

@@ -265,19 +265,29 @@ int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* s
 // ------------------------------------------------------------------------------------------------
 // GT packing: rows -> (B,G,725) padded, in px (utils/loss.py:215-239, 834-844).  Slot of row n inside
 // its image = number of earlier rows with the same image index (stable, as `targets[matches]`).
+// The image indices are first gathered into a compact array (one strided read per row), so the rank of a row
+// is a scan of contiguous ints, not of the 726-float rows themselves.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out) {
+__global__ void k_pack_index(const float* __restrict__ head, int64_t hs, int N, int* __restrict__ idx) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) idx[n] = (int)head[(int64_t)n * hs];
+}
+
+// head: [image index, class, x, y, w, h] per row (hs floats apart); seg: 720 contour values per row (ss floats apart)
+__global__ void __launch_bounds__(128) k_pack_targets(const float* __restrict__ head, int64_t hs, const float* __restrict__ seg, int64_t ss,
+                                                      const int* __restrict__ idx, int N, int B, int G, float img_w, float img_h,
+                                                      float* __restrict__ out) {
     const int n = blockIdx.x;
-    const float* t = targets + (int64_t)n * rs;
-    const int b = (int)t[0];
-    __shared__ int s_slot;
-    if (threadIdx.x == 0) s_slot = 0;
-    __syncthreads();
+    const float* t = head + (int64_t)n * hs;
+    const float* sg = seg + (int64_t)n * ss;
+    const int b = idx[n];
+    __shared__ int s_part[4];
     int cnt = 0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) cnt += ((int)targets[(int64_t)k * rs] == b) ? 1 : 0;
-    if (cnt) atomicAdd(&s_slot, cnt);
+    for (int k = threadIdx.x; k < n; k += 128) cnt += (idx[k] == b) ? 1 : 0;
+    cnt = (int)warp_sum((float)cnt);   // (n < 2^24: exact)
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = cnt;
     __syncthreads();
-    const int slot = s_slot;
+    const int slot = s_part[0] + s_part[1] + s_part[2] + s_part[3];
     if (b < 0 || b >= B || slot >= G) return;
     float* row = out + ((int64_t)b * G + slot) * (5 + 2 * YCR_C);
     if (threadIdx.x == 0) {
@@ -287,15 +297,20 @@ __global__ void k_pack_targets(const float* targets, int64_t rs, int N, int B, i
     }
     // the reference scales the first 360 contour values by width and the last 360 by height although
     // the data is x,y-interleaved (utils/loss.py:236-237); restated literally
-    for (int k = threadIdx.x; k < 2 * YCR_C; k += blockDim.x) row[5 + k] = t[6 + k] * ((k < YCR_C) ? img_w : img_h);
+    for (int k = threadIdx.x; k < 2 * YCR_C; k += 128) row[5 + k] = sg[k] * ((k < YCR_C) ? img_w : img_h);
 }
 
-int launch_pack_targets(const float* targets, int64_t rs, int N, int B, int G, float img_w, float img_h, float* out,
-                        cudaStream_t st) {
+int launch_pack_targets(const float* head, int64_t hs, const float* seg, int64_t ss, int N, int B, int G, float img_w, float img_h,
+                        float* out, cudaStream_t st) {
+    // the padded tensor must be zero where no row lands; the compact index array comes from the stream-ordered pool
     YCR_CUDA_CHECK(cudaMemsetAsync(out, 0, (size_t)B * G * (5 + 2 * YCR_C) * sizeof(float), st));
     if (N > 0) {
-        k_pack_targets<<<N, 128, 0, st>>>(targets, rs, N, B, G, img_w, img_h, out);
+        int* idx = nullptr;
+        YCR_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&idx), (size_t)N * sizeof(int), st));
+        k_pack_index<<<(N + 255) / 256, 256, 0, st>>>(head, hs, N, idx);
+        k_pack_targets<<<N, 128, 0, st>>>(head, hs, seg, ss, idx, N, B, G, img_w, img_h, out);
         YCR_LAUNCH_CHECK();
+        YCR_CUDA_CHECK(cudaFreeAsync(idx, st));
     }
     return YCR_OK;
 }

@@ -35,17 +35,37 @@ def decode(feats, strides, nc: int, R: int = 36):
     return out
 
 
+def _default_act():
+    """The activation the model definition selected: parse_model sets `Conv.default_act` from the yaml's `activation:`
+    key (nn/tasks.py:668-671; the reference's own yolov8-seg.yaml asks for nn.ReLU()).  SiLU, the class default of
+    nn/modules/conv.py, when no `ultralytics` is loaded."""
+    import copy
+    import sys
+    conv_mod = sys.modules.get("ultralytics.nn.modules.conv")
+    act = getattr(getattr(conv_mod, "Conv", None), "default_act", None) if conv_mod is not None else None
+    return copy.deepcopy(act) if isinstance(act, nn.Module) else nn.SiLU()
+
+
 class _ConvBnSiLU(nn.Module):
-    """Conv2d + BatchNorm2d + SiLU, the block the head stacks (ultralytics nn/modules/conv.py Conv)."""
+    """Conv2d + BatchNorm2d + activation (SiLU by default), the block the head stacks (nn/modules/conv.py Conv)."""
 
     def __init__(self, c1, c2, k=3):
         super().__init__()
         self.conv = nn.Conv2d(c1, c2, k, 1, k // 2, bias=False)
         self.bn = nn.BatchNorm2d(c2)
-        self.act = nn.SiLU()
+        self.act = _default_act()
 
     def forward(self, x):
         return self.act(self.bn(self.conv(x)))
+
+
+class _NoProto(int):
+    """The third element of the eval output.  The reference returns the int 1 there (nn/modules/head.py:570), and its
+    own predictor then indexes it as a proto tensor (models/yolo/segment/predict.py:26,39: `proto[i]`), which raises
+    as soon as an image has a detection.  This is still the int 1, but it can be indexed."""
+
+    def __getitem__(self, i):
+        return self
 
 
 class Segment(nn.Module):
@@ -70,6 +90,8 @@ class Segment(nn.Module):
         self.reg_max = 16
         self.no = nc + nm
         self.stride = torch.zeros(self.nl)
+        self.anchors = torch.empty(0)   # BaseModel._apply moves stride / anchors / strides of the head (nn/tasks.py:184-187)
+        self.strides = torch.empty(0)
         c2, c3 = max((16, ch[0] // 4, self.reg_max * 4)), max(ch[0], min(self.nc, 100))
         self.cv2 = nn.ModuleList(nn.Sequential(_ConvBnSiLU(x, c2, 3), _ConvBnSiLU(c2, c2, 3), nn.Conv2d(c2, self.nm, 1))
                                  for x in ch)
@@ -90,4 +112,4 @@ class Segment(nn.Module):
         if self.training:
             return feats, 5, 2
         allpred = decode(feats, self.stride.tolist(), self.nc, self.nm)
-        return allpred, (feats, allpred, 1)
+        return allpred, (feats, allpred, _NoProto(1))

@@ -113,7 +113,8 @@ class v8SegmentationLoss:
 
     # -- GT packing: utils/loss.py:834-844 + preprocess utils/loss.py:215-239 ----------------------
     def _staging(self, n_rows):
-        """(n_rows, 726) view of a pinned host buffer; waits until the copy that last read it has finished."""
+        """Pinned host buffer for n_rows GT rows: 6 header floats + 720 contour floats per row, header block first.
+        Waits until the copy that last read the buffer has finished."""
         ev = getattr(self, "_stage_ev", None)
         if ev is not None:
             ev.synchronize()
@@ -122,7 +123,7 @@ class v8SegmentationLoss:
         if buf is None or buf.numel() < n_rows * 726:
             buf = torch.empty(max(n_rows, 64) * 726, dtype=torch.float32).pin_memory()
             self._stage_buf = buf
-        return buf[:n_rows * 726].view(n_rows, 726)
+        return buf[:n_rows * 726]
 
     @property
     def last_gt_copy_event(self):
@@ -132,38 +133,73 @@ class v8SegmentationLoss:
         return getattr(self, "_stage_ev", None)
 
     def pack_targets(self, batch, batch_size, img_hw):
-        """-> (packed (B,G,725) device tensor, candidate upper bound).  The rows are assembled on the host
-        (they arrive there from the dataloader), copied once, and padded/scaled by a kernel."""
+        """-> (packed (B,G,725) device tensor, candidate upper bound).  The rows arrive on the host from the
+        dataloader: `batch['segments']` is concatenated straight into a pinned staging buffer (the one host pass over
+        the contours), the six header columns next to it, one H2D copy, and a kernel pads and scales them."""
         dev = self.device
-        bi = batch["batch_idx"].view(-1).float()
+        bi = batch["batch_idx"].view(-1)
         N = bi.numel()
         h, w = float(img_hw[0]), float(img_hw[1])
         if N == 0:
             return torch.zeros(batch_size, 0, 5 + 720, device=dev), 0
         segs = batch["segments"]
-        seg = (torch.cat(list(segs)) if isinstance(segs, (list, tuple)) else segs).reshape(-1, 720).float()
-        cls = batch["cls"].reshape(-1).float()
-        bb = batch["bboxes"].reshape(-1, 4).float()
-        bi_h = bi.cpu()
-        G = int(torch.bincount(bi_h.long(), minlength=batch_size).max())
-        bb_h = bb.cpu()
-        xyxy = torch.stack([(bb_h[:, 0] - bb_h[:, 2] / 2) * w, (bb_h[:, 1] - bb_h[:, 3] / 2) * h,
-                            (bb_h[:, 0] + bb_h[:, 2] / 2) * w, (bb_h[:, 1] + bb_h[:, 3] / 2) * h], 1).contiguous()
+        lib = L.lib()
         cgrid = L.make_grid(self._shapes, self.stride_list)
-        cap = int(L.lib().ycr_candidate_bound_h(C.byref(cgrid), xyxy.data_ptr(), 4, N)) + 64
-        parts = [bi.view(-1, 1).to(seg.device), cls.view(-1, 1).to(seg.device), bb.to(seg.device), seg]
-        if seg.device.type == "cpu":
-            # assemble the rows in a pinned staging buffer so that the one H2D copy is really asynchronous
-            # (a pageable source makes the host wait for everything queued on the copy engine before it)
-            rows = torch.cat(parts, 1, out=self._staging(N)).to(dev, non_blocking=True)
+        seg_list = list(segs) if isinstance(segs, (list, tuple)) else [segs]
+        on_host = all(t.device.type == "cpu" for t in seg_list) and bi.device.type == "cpu"
+        if on_host:
+            stage = self._staging(N)
+            head = stage[:N * 6].view(N, 6)
+            seg = stage[N * 6:].view(N, 720)
+            srcs = [t.reshape(-1, 720) for t in seg_list]
+            if all(t.dtype == torch.float32 for t in srcs):
+                torch.cat(srcs, 0, out=seg)
+            else:
+                seg.copy_(torch.cat(srcs, 0))
+            head[:, 0] = bi
+            head[:, 1] = batch["cls"].view(-1)
+            head[:, 2:6] = batch["bboxes"].view(-1, 4)
+            G = int(torch.bincount(bi.long(), minlength=batch_size).max())
+            cap = int(lib.ycr_candidate_bound_xywhn_h(C.byref(cgrid), head.data_ptr() + 8, 6, N, w, h)) + 64
+            # The copy goes on its own stream into one of two persistent device buffers: the host runs ahead of the
+            # device, so the rows of step k+1 cross the bus while the kernels of step k still run.  The compute
+            # stream waits for the copy; the copy waits until the kernel that last read this buffer has finished.
+            cur = torch.cuda.current_stream(dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+                self._rows_dev = [None, None]
+                self._rows_free = [None, None]
+                self._rows_turn = 0
+            k = self._rows_turn = 1 - self._rows_turn
+            if self._rows_dev[k] is None or self._rows_dev[k].numel() < stage.numel():
+                self._rows_dev[k] = torch.empty(max(stage.numel(), 64 * 726), device=dev, dtype=torch.float32)
+                self._rows_free[k] = None
+            rows = self._rows_dev[k][:stage.numel()]
+            cs = self._copy_stream
+            if self._rows_free[k] is not None:
+                cs.wait_event(self._rows_free[k])
+            with torch.cuda.stream(cs):
+                rows.copy_(stage, non_blocking=True)
             self._stage_ev = torch.cuda.Event()
-            self._stage_ev.record(torch.cuda.current_stream(dev))
+            self._stage_ev.record(cs)
+            cur.wait_event(self._stage_ev)
+            self._rows_slot = k
         else:
-            rows = torch.cat(parts, 1).to(dev, non_blocking=True).contiguous()
+            seg = torch.cat([t.reshape(-1, 720) for t in seg_list], 0).float().to(dev)
+            head = torch.cat((bi.view(-1, 1).float().to(dev), batch["cls"].view(-1, 1).float().to(dev),
+                              batch["bboxes"].view(-1, 4).float().to(dev)), 1)
+            G = int(torch.bincount(bi.long().cpu(), minlength=batch_size).max())
+            bb_h = head[:, 2:6].cpu().contiguous()
+            cap = int(lib.ycr_candidate_bound_xywhn_h(C.byref(cgrid), bb_h.data_ptr(), 4, N, w, h)) + 64
+            rows = torch.cat((head.reshape(-1), seg.reshape(-1)))
         out = torch.empty(batch_size, G, 5 + 720, device=dev)
-        rc = L.lib().ycr_pack_targets(rows.data_ptr(), rows.stride(0), N, batch_size, G, w, h, out.data_ptr(),
-                                      L.stream_ptr(dev))
-        L.check(rc, "ycr_pack_targets")
+        rc = lib.ycr_pack_targets_split(rows.data_ptr(), 6, rows.data_ptr() + N * 6 * 4, 720, N, batch_size, G, w, h,
+                                        out.data_ptr(), L.stream_ptr(dev))
+        L.check(rc, "ycr_pack_targets_split")
+        if on_host:   # the staged rows may be overwritten once this kernel has read them
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self._rows_free[self._rows_slot] = ev
         return out, cap
 
     def __call__(self, preds, batch):
