@@ -62,7 +62,7 @@ def model_yaml() -> str:
     return os.path.join(REF_DIR, "yolov8-seg.yaml")
 
 
-def reference_criterion(nc, rays, strides, box=7.5, cls=0.5):
+def reference_criterion(nc, rays, strides, box=7.5, cls=0.5, device="cpu"):
     """The reference's v8SegmentationLoss (utils/loss.py:772) on the CPU, built on a stub of the two objects its
     constructor reads (`model.args`, `model.model[-1]`), so the loss path can be driven without the conv backbone."""
     from types import SimpleNamespace
@@ -83,4 +83,4 @@ def reference_criterion(nc, rays, strides, box=7.5, cls=0.5):
             self.model = torch.nn.ModuleList([_Head()])
             self.args = SimpleNamespace(box=box, cls=cls, dfl=1.5, overlap_mask=True)
 
-    return rloss.v8SegmentationLoss(_Model())
+    return rloss.v8SegmentationLoss(_Model().to(device))

@@ -315,41 +315,71 @@ def run_ours(args):
     copy_stream = torch.cuda.Stream(dev)
     pending = {}
 
-    def issue_copy():
-        gt_ev = crit.last_gt_copy_event   # this step's GT rows go first (its kernels wait for them)
-        if gt_ev is not None:
-            copy_stream.wait_event(gt_ev)
-        with torch.cuda.stream(copy_stream):
-            fd = [f.to(dev, non_blocking=True) for f in feats_h]
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        pending["next"] = (fd, ev)
+    def run_e2e(host_feats, n_steps):
+        """K steps through the public API from pinned HOST feature maps (copied H2D inside the timed region, double
+        buffered) and the CPU batch dict; the loss is read back every step.  -> milliseconds for n_steps."""
+        def issue():
+            gt_ev = crit.last_gt_copy_event   # this step's GT rows go first (its kernels wait for them)
+            if gt_ev is not None:
+                copy_stream.wait_event(gt_ev)
+            with torch.cuda.stream(copy_stream):
+                fd = [f.to(dev, non_blocking=True) for f in host_feats]
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            pending["next"] = (fd, ev)
 
-    issue_copy()
+        def one():
+            fd, ev = pending["next"]
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            for f in fd:
+                f.record_stream(cur)
+            fd = [f.requires_grad_(True) for f in fd]
+            total, items = crit((fd, 5, 2), batch)
+            total.backward()
+            issue()
+            return float(total.detach())  # D2H read of the step's result
 
-    def step_e2e():
-        fd, ev = pending["next"]
-        cur = torch.cuda.current_stream(dev)
-        cur.wait_event(ev)
-        for f in fd:
-            f.record_stream(cur)
-        fd = [f.requires_grad_(True) for f in fd]
-        total, items = crit((fd, 5, 2), batch)
+        issue()
+        for _ in range(3):
+            one()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            one()
+        e1.record()
+        barrier()
+        pending.clear()
+        return e0.elapsed_time(e1)
+
+    e_steps = max(3, min(args.steps, 10))
+    ms_e2e = run_e2e(feats_h, e_steps)
+
+    # ---- the same with fp16 head outputs, what the head emits under autocast (the reference's default,
+    # engine/trainer.py:332): the kernels read the half maps in place and write half gradients ----
+    feats_h16 = [f.half().pin_memory() for f in feats_cpu]
+    feats_d16 = [f.to(dev).requires_grad_(True) for f in feats_h16]
+
+    def step_resident16():
+        for f in feats_d16:
+            f.grad = None
+        total, items = crit((feats_d16, 5, 2), batch)
         total.backward()
-        issue_copy()
-        return float(total.detach())  # D2H read of the step's result
 
     for _ in range(3):
-        step_e2e()
+        step_resident16()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e_steps = max(3, min(args.steps, 10))
-    e0.record()
-    for _ in range(e_steps):
-        step_e2e()
-    e1.record()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h_steps = max(3, min(args.steps, 20))
+    h0.record()
+    for _ in range(h_steps):
+        step_resident16()
+    h1.record()
     barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    ms_res16 = h0.elapsed_time(h1)
+    ms_e2e16 = run_e2e(feats_h16, e_steps)
+    del feats_d16
 
     # ---- inference path (config C3), reported alongside ----
     icfg = synth.CONFIGS["C3"]
@@ -379,7 +409,7 @@ def run_ours(args):
     kept = sum(d.shape[0] for d in dets) / ib
 
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([ms_total, ms_e2e, ms_inf], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, ms_e2e, ms_inf, ms_res16, ms_e2e16], device=dev, dtype=torch.float64)
     per_rank = None
     if use_dist:
         import torch.distributed as dist
@@ -388,7 +418,7 @@ def run_ours(args):
         per_rank = {"ms_per_step": [float(g[0]) / args.steps for g in gathered],
                     "e2e_ms_per_step": [float(g[1]) / e_steps for g in gathered]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_inf = [float(x) for x in t.tolist()]
+    ms_total, ms_e2e, ms_inf, ms_res16, ms_e2e16 = [float(x) for x in t.tolist()]
     if rank != 0:
         if use_dist:
             import torch.distributed as dist
@@ -446,6 +476,11 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4, "steps": e_steps},
         # per step: k_pack_index, k_pack_targets, k_gt_rects, k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image,
         # k_positive_gather, k_loss_stream_v4, k_loss_finalize, k_scale (torch's fills and copies are not counted)
+        "fp16_inputs": {"note": "same workload with fp16 head outputs (autocast, the reference's default): maps read in place, "
+                                "fp32 arithmetic, fp16 gradients",
+                        "value": world * B / (ms_res16 / h_steps / 1e3), "ms_per_step": ms_res16 / h_steps,
+                        "e2e": {"value": world * B / (ms_e2e16 / e_steps / 1e3), "unit": "images/s",
+                                "h2d_bytes_per_step": in_bytes // 2 + gt_rows_bytes, "d2h_bytes_per_step": 4}},
         "gpu_launches": 11 * args.steps,
         "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
                   "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",

@@ -167,6 +167,16 @@ int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, floa
                          float* loss_out, void* workspace, size_t workspace_bytes, int64_t cand_capacity,
                          void* stream);
 
+/* Same for feature maps of element type `dtype` (0 fp32, 1 fp16, 2 bf16) - what the head emits under autocast, the
+ * reference's default (engine/trainer.py:332).  The maps are read in place, arithmetic is fp32 as in the reference
+ * (its sigmoid and its BCE targets are rounded to the input type, utils/loss.py:861,867 - so are they here), and
+ * grad_feats are written in the input type. */
+int ycr_seg_loss_fwd_bwd_dt(const ycr_grid_t* grid, const void* const* feats, void* const* grad_feats, int dtype,
+                            const ycr_gt_t* gt, const ycr_assign_cfg_t* acfg, const ycr_loss_cfg_t* lcfg, float* loss_out,
+                            void* workspace, size_t workspace_bytes, int64_t cand_capacity, void* stream);
+int ycr_scale_grads_dt(const ycr_grid_t* grid, int B, int channels, void* const* grad_feats, int dtype, const float* scale_d,
+                       void* stream);
+
 /* In-place grad *= *scale_d for the three gradient maps; returns immediately on the device when
  * *scale_d == 1 (the common loss.backward() case), so autograd's upstream gradient costs no pass. */
 int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* grad_feats,
@@ -214,6 +224,11 @@ int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc,
  * ycr_nms_cfg_t.best_class it saves single-label NMS the read of all class rows. */
 int ycr_decode_best(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred,
                     void* best_class_out, void* stream);
+
+/* Same for feature maps of element type `dtype` (0 fp32, 1 fp16, 2 bf16: the validator runs the model in half,
+ * engine/validator.py:103-104); arithmetic and allpred stay fp32.  best_class_out may be NULL. */
+int ycr_decode_dt(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, float* allpred,
+                  void* best_class_out, void* stream);
 
 typedef struct {
     float conf_thres, iou_thres;

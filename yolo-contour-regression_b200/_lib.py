@@ -75,6 +75,11 @@ EXPORTS = {
     "ycr_seg_loss_fwd_bwd": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                        C.POINTER(Gt), C.POINTER(AssignCfg), C.POINTER(LossCfg), C.c_void_p,
                                        C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]),
+    "ycr_seg_loss_fwd_bwd_dt": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int,
+                                          C.POINTER(Gt), C.POINTER(AssignCfg), C.POINTER(LossCfg), C.c_void_p,
+                                          C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p]),
+    "ycr_scale_grads_dt": (C.c_int, [C.POINTER(Grid), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_void_p,
+                                     C.c_void_p]),
     "ycr_scale_grads": (C.c_int, [C.POINTER(Grid), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]),
     "ycr_pack_targets": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p]),
@@ -92,6 +97,8 @@ EXPORTS = {
     "ycr_mask_iou_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "ycr_mask_iou": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_void_p,
                                C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ycr_decode_dt": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_void_p]),
     "ycr_nms_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg)]),
     "ycr_nms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg), C.c_void_p, C.c_void_p,
                           C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -125,6 +132,9 @@ def check(rc: int, what: str):
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise YcrError(f"{what} failed ({rc}): {msg}")
+
+
+DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 
 def stream_ptr(device) -> int:

@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/ycr_b200.h.  Thin argument checking + kernel sequencing;
 // no torch types, no CPU fallbacks.
 #include "train_path.cuh"
+#include "dtype.cuh"
 #include <stdarg.h>
 #include <string.h>
 
@@ -41,10 +42,10 @@ int launch_bbox_loss(const float* pred_dist, const float* pred_bboxes, const flo
                      const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, const float* tss_d,
                      int B, int A, int nc, int reg_max, int use_dfl, float* loss_out, float* grad_dist, float* grad_bboxes,
                      void* workspace, size_t workspace_bytes, cudaStream_t st);
-int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* scale, cudaStream_t st);
+int launch_scale(void* const* p, const int64_t* n, int n_levels, int dtype, const float* scale, cudaStream_t st);
 int launch_pack_targets(const float* head, int64_t hs, const float* seg, int64_t ss, int N, int B, int G, float img_w, float img_h,
                         float* out, cudaStream_t st);
-int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, int2* best,
+int launch_decode(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, float* allpred, int2* best,
                   cudaStream_t st);
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg);
 int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
@@ -194,10 +195,11 @@ int ycr_assign(const ycr_grid_t* grid, const ycr_pred_view_t* pred, const ycr_gt
     return launch_assign_dense(a, ws, *out, st);
 }
 
-int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, float* const* grad_feats, const ycr_gt_t* gt,
-                         const ycr_assign_cfg_t* acfg, const ycr_loss_cfg_t* lcfg, float* loss_out, void* workspace,
-                         size_t workspace_bytes, int64_t cand_capacity, void* stream) {
+int ycr_seg_loss_fwd_bwd_dt(const ycr_grid_t* grid, const void* const* feats, void* const* grad_feats, int dtype,
+                            const ycr_gt_t* gt, const ycr_assign_cfg_t* acfg, const ycr_loss_cfg_t* lcfg, float* loss_out,
+                            void* workspace, size_t workspace_bytes, int64_t cand_capacity, void* stream) {
     if (!feats || !gt || !lcfg || !loss_out || !workspace) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (dtype != YCR_F32 && dtype != YCR_F16 && dtype != YCR_BF16) { ycr_set_error("dtype %d: 0 f32, 1 f16, 2 bf16", dtype); return YCR_E_ARG; }
     int rc = check_common(grid, acfg, gt->B, gt->G);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -206,11 +208,14 @@ int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, floa
     a.gt = *gt;
     a.cfg = *acfg;
     a.pc = make_polar_const(acfg->rays);
+    a.dtype = dtype;
     const int R = acfg->rays, nc = acfg->num_classes;
+    const int esz = ycr_dtype_size(dtype);
     for (int l = 0; l < grid->n_levels; ++l) {
         const int64_t hw = (int64_t)grid->h[l] * grid->w[l];
-        a.pred.rays[l] = feats[l];
-        a.pred.cls[l] = feats[l] + (int64_t)R * hw;
+        // (the view's pointers are typed float*; the kernels index them as arrays of `dtype` elements)
+        a.pred.rays[l] = reinterpret_cast<const float*>(feats[l]);
+        a.pred.cls[l] = reinterpret_cast<const float*>(reinterpret_cast<const char*>(feats[l]) + (int64_t)R * hw * esz);
         a.pred.rays_sb[l] = a.pred.cls_sb[l] = (int64_t)(R + nc) * hw;
         a.pred.rays_sa[l] = a.pred.cls_sa[l] = 1;
         a.pred.rays_sc[l] = a.pred.cls_sc[l] = hw;
@@ -225,13 +230,26 @@ int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, floa
     return launch_loss_stream(a, ws, feats, grad_feats, *lcfg, loss_out, st);
 }
 
-int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* grad_feats, const float* scale_d, void* stream) {
+int ycr_seg_loss_fwd_bwd(const ycr_grid_t* grid, const float* const* feats, float* const* grad_feats, const ycr_gt_t* gt,
+                         const ycr_assign_cfg_t* acfg, const ycr_loss_cfg_t* lcfg, float* loss_out, void* workspace,
+                         size_t workspace_bytes, int64_t cand_capacity, void* stream) {
+    return ycr_seg_loss_fwd_bwd_dt(grid, reinterpret_cast<const void* const*>(feats), reinterpret_cast<void* const*>(grad_feats),
+                                   YCR_F32, gt, acfg, lcfg, loss_out, workspace, workspace_bytes, cand_capacity, stream);
+}
+
+int ycr_scale_grads_dt(const ycr_grid_t* grid, int B, int channels, void* const* grad_feats, int dtype, const float* scale_d,
+                       void* stream) {
     if (!grid || !grad_feats || !scale_d) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (dtype != YCR_F32 && dtype != YCR_F16 && dtype != YCR_BF16) { ycr_set_error("dtype %d: 0 f32, 1 f16, 2 bf16", dtype); return YCR_E_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int64_t n[YCR_MAX_LEVELS] = {0};
     if (grid->n_levels > YCR_MAX_LEVELS) { ycr_set_error("too many levels"); return YCR_E_ARG; }
     for (int l = 0; l < grid->n_levels; ++l) n[l] = (int64_t)B * channels * grid->h[l] * grid->w[l];
-    return launch_scale(grad_feats, n, grid->n_levels, scale_d, st);
+    return launch_scale(grad_feats, n, grid->n_levels, dtype, scale_d, st);
+}
+
+int ycr_scale_grads(const ycr_grid_t* grid, int B, int channels, float* const* grad_feats, const float* scale_d, void* stream) {
+    return ycr_scale_grads_dt(grid, B, channels, reinterpret_cast<void* const*>(grad_feats), YCR_F32, scale_d, stream);
 }
 
 int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int G, float img_w, float img_h,
@@ -275,14 +293,24 @@ int ycr_bbox_loss_fwd_bwd(const float* pred_dist, const float* pred_bboxes, cons
 int ycr_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, void* stream) {
     if (!grid || !feats || !allpred) { ycr_set_error("null argument"); return YCR_E_ARG; }
     if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
-    return launch_decode(grid, feats, B, nc, R, allpred, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    return launch_decode(grid, reinterpret_cast<const void* const*>(feats), YCR_F32, B, nc, R, allpred, nullptr,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ycr_decode_best(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred,
                     void* best_class_out, void* stream) {
     if (!grid || !feats || !allpred || !best_class_out) { ycr_set_error("null argument"); return YCR_E_ARG; }
     if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
-    return launch_decode(grid, feats, B, nc, R, allpred, reinterpret_cast<int2*>(best_class_out),
+    return launch_decode(grid, reinterpret_cast<const void* const*>(feats), YCR_F32, B, nc, R, allpred,
+                         reinterpret_cast<int2*>(best_class_out), reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ycr_decode_dt(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, float* allpred,
+                  void* best_class_out, void* stream) {
+    if (!grid || !feats || !allpred) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
+    if (dtype != YCR_F32 && dtype != YCR_F16 && dtype != YCR_BF16) { ycr_set_error("dtype %d: 0 f32, 1 f16, 2 bf16", dtype); return YCR_E_ARG; }
+    return launch_decode(grid, feats, dtype, B, nc, R, allpred, reinterpret_cast<int2*>(best_class_out),
                          reinterpret_cast<cudaStream_t>(stream));
 }
 

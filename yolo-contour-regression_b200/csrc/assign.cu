@@ -330,13 +330,13 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             ay = anchor_coord(ap.iy, a.grid.stride[ap.level]);
             const int b = bg / a.gt.G;
             const int l = ap.level;
-            const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+            const int64_t r0 = (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
             const int64_t sc = a.pred.rays_sc[l];
 #pragma unroll
-            for (int i = 0; i < R; ++i) pr[i] = rp[i * sc];
+            for (int i = 0; i < R; ++i) pr[i] = ycr_ld(a.pred.rays[l], r0 + i * sc, a.dtype);
             const int label = (int)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
-            score = a.pred.cls[l][(int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
-                                  (int64_t)label * a.pred.cls_sc[l]];
+            score = ycr_ld(a.pred.cls[l], (int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
+                                          (int64_t)label * a.pred.cls_sc[l], a.dtype);
             polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
         }
         if (tid < 32) fetch_next(drawn);
@@ -358,13 +358,14 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             float smin = 0.f, smax = 0.f;
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                const float p = pr[i] * rs;
+                const float p = ycr_round_to(pr[i] * rs, a.dtype);   // the reference multiplies in the input type
                 const float t = sm.tv(i, tid);
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
             const float ov = smin / smax;
-            if (a.pred.cls_is_logit) score = 1.f / (1.f + expf(-score));
+            // `pred_scores.detach().sigmoid()` stays in the input type (utils/loss.py:861)
+            if (a.pred.cls_is_logit) score = ycr_round_to(1.f / (1.f + expf(-score)), a.dtype);
             if (ws.cand_t) {
                 float* tp = ws.cand_t + (int64_t)work * R * NT + tid;
 #pragma unroll 4
@@ -730,13 +731,13 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
         if (pa.centerness && grow < pa.pos_capacity) pa.centerness[grow] = sqrtf(tmin / tmax);
         if (pa.with_loss) {
             const int l = ap.level;
-            const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+            const int64_t r0 = (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
             const int64_t sc = a.pred.rays_sc[l];
             const float rs = a.pred.ray_scale[l];
             float mn[R], mx[R];
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                const float p = rp[i * sc] * rs;
+                const float p = ycr_round_to(ycr_ld(a.pred.rays[l], r0 + i * sc, a.dtype) * rs, a.dtype);
                 const float t = sm.tv(i, tid);
                 mn[i] = fmaxf(fminf(p, t), YCR_FLOOR);
                 mx[i] = fmaxf(p, t);
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(NT) k_positive_targets(const __grid_constant__
             const float imax = 1.f / smax, imin = 1.f / smin;
             float* gp = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
             for (int i = 0; i < R; ++i) {
-                const float p = rp[i * sc] * rs;
+                const float p = ycr_round_to(ycr_ld(a.pred.rays[l], r0 + i * sc, a.dtype) * rs, a.dtype);
                 const float t = sm.tv(i, tid);
                 float g = 0.f;
                 if (p >= t) g += imax;                       // max() routes to pred (first index on ties)
@@ -804,14 +805,14 @@ __global__ void __launch_bounds__(256) k_positive_gather(const __grid_constant__
     const AnchorPos ap = anchor_pos(a.grid, an);
     const int l = ap.level;
     // the predictions do not depend on the candidate lookup: request them first
-    const float* rp = a.pred.rays[l] + (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
+    const int64_t r0 = (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
     const int64_t sc = a.pred.rays_sc[l];
     const float rs = a.pred.ray_scale[l];
     float p[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
         const int i = lane + 32 * k;
-        p[k] = (pa.with_loss && i < R) ? rp[i * sc] * rs : 0.f;
+        p[k] = (pa.with_loss && i < R) ? ycr_round_to(ycr_ld(a.pred.rays[l], r0 + i * sc, a.dtype) * rs, a.dtype) : 0.f;
     }
     const float w = ws.pos_norm[prow];
     const float tss = pa.tss[0];

@@ -3,6 +3,7 @@
 // (utils/ops.py:407) as a sorted, chunked block-bitmask greedy suppression.
 // Paths under /root/reference/ultralytics-main/ultralytics/.
 #include "common.cuh"
+#include "dtype.cuh"
 #include <math.h>
 
 // ------------------------------------------------------------------------------------------------
@@ -13,8 +14,8 @@
 // ------------------------------------------------------------------------------------------------
 struct DecodeArgs {
     GridDev grid;
-    const float* feats[YCR_MAX_LEVELS];
-    int B, nc, R;
+    const void* feats[YCR_MAX_LEVELS];   // element type `dtype` (fp32 / fp16 / bf16); arithmetic and output are fp32
+    int B, nc, R, dtype;
     float cs[2 * 72];  // cos[0..R), sin[0..R)
 };
 
@@ -34,12 +35,12 @@ __global__ void __launch_bounds__(256) k_decode(const __grid_constant__ DecodeAr
     const float ax = ((float)ix + 0.5f) * stride, ay = ((float)iy + 0.5f) * stride;
     const int R = d.R, nc = d.nc;
     const int CH = 4 + nc + 3 * R;
-    const float* f = d.feats[l] + (int64_t)b * (R + nc) * hw + al;
+    const int64_t f0 = (int64_t)b * (R + nc) * hw + al;
     float* o = out + (int64_t)b * CH * A + an;
     float minx = 3.4e38f, miny = 3.4e38f, maxx = -3.4e38f, maxy = -3.4e38f;
 #pragma unroll 4
     for (int i = 0; i < R; ++i) {
-        const float dist = fmaxf(__fmul_rn(f[(int64_t)i * hw], stride), YCR_FLOOR);
+        const float dist = fmaxf(__fmul_rn(ycr_ld(d.feats[l], f0 + (int64_t)i * hw, d.dtype), stride), YCR_FLOOR);
         const float x = __fadd_rn(__fmul_rn(dist, d.cs[i]), ax);
         const float y = __fadd_rn(__fmul_rn(dist, d.cs[R + i]), ay);
         minx = fminf(minx, x); maxx = fmaxf(maxx, x);
@@ -52,10 +53,9 @@ __global__ void __launch_bounds__(256) k_decode(const __grid_constant__ DecodeAr
     o[(int64_t)A] = miny;
     o[(int64_t)2 * A] = maxx;
     o[(int64_t)3 * A] = maxy;
-    const float* fc = f + (int64_t)R * hw;
 #pragma unroll 4
     for (int c = 0; c < nc; ++c) {
-        const float x = fc[(int64_t)c * hw];
+        const float x = ycr_ld(d.feats[l], f0 + (int64_t)(R + c) * hw, d.dtype);
         o[(int64_t)(4 + c) * A] = 1.f / (1.f + expf(-x));
     }
 }
@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) k_decode(const __grid_constant__ DecodeAr
 // Vectorised variant: one thread per four consecutive anchors of a row (W_l and H_l*W_l multiples of 4),
 // 128-bit loads/stores.  Split in two kernels so that the class part (pure streaming sigmoid) is not
 // held to the occupancy of the ray part (which carries the 16 running box extrema).
+template <typename T>
 __global__ void __launch_bounds__(256, 3) k_decode_rays_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
     const int A = d.grid.off[YCR_MAX_LEVELS];
     const int b = blockIdx.y;
@@ -81,13 +82,13 @@ __global__ void __launch_bounds__(256, 3) k_decode_rays_v4(const __grid_constant
     const float ax2 = ((float)(ix + 2) + 0.5f) * stride, ax3 = ((float)(ix + 3) + 0.5f) * stride;
     const int R = d.R, nc = d.nc;
     const int CH = 4 + nc + 3 * R;
-    const float* f = d.feats[l] + (int64_t)b * (R + nc) * hw + al;
+    const T* f = reinterpret_cast<const T*>(d.feats[l]) + (int64_t)b * (R + nc) * hw + al;
     float* o = out + (int64_t)b * CH * A + an;
     float4 minx = make_float4(3.4e38f, 3.4e38f, 3.4e38f, 3.4e38f), miny = minx;
     float4 maxx = make_float4(-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f), maxy = maxx;
 #pragma unroll 2
     for (int i = 0; i < R; ++i) {
-        const float4 r = __ldcs(reinterpret_cast<const float4*>(f + (int64_t)i * hw));
+        const float4 r = YcrType<T>::ld4cs(f + (int64_t)i * hw);
         const float c = d.cs[i], s = d.cs[R + i];
         float4 dist, x, y, v;
         dist.x = fmaxf(__fmul_rn(r.x, stride), YCR_FLOOR); dist.y = fmaxf(__fmul_rn(r.y, stride), YCR_FLOOR);
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256, 3) k_decode_rays_v4(const __grid_constant
 }
 
 // class rows: grid (anchor groups, class groups of 8, B)
+template <typename T>
 __global__ void __launch_bounds__(256) k_decode_cls_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out) {
     const int A = d.grid.off[YCR_MAX_LEVELS];
     const int b = blockIdx.z;
@@ -127,11 +129,11 @@ __global__ void __launch_bounds__(256) k_decode_cls_v4(const __grid_constant__ D
     const int R = d.R, nc = d.nc;
     const int CH = 4 + nc + 3 * R;
     const int c0 = blockIdx.y * 8, c1 = min(nc, c0 + 8);
-    const float* fc = d.feats[l] + (int64_t)b * (R + nc) * hw + (int64_t)R * hw + al;
+    const T* fc = reinterpret_cast<const T*>(d.feats[l]) + (int64_t)b * (R + nc) * hw + (int64_t)R * hw + al;
     float* o = out + (int64_t)b * CH * A + an;
 #pragma unroll 8
     for (int c = c0; c < c1; ++c) {
-        const float4 x = __ldcs(reinterpret_cast<const float4*>(fc + (int64_t)c * hw));
+        const float4 x = YcrType<T>::ld4cs(fc + (int64_t)c * hw);
         float4 p;
         p.x = 1.f / (1.f + expf(-x.x)); p.y = 1.f / (1.f + expf(-x.y));
         p.z = 1.f / (1.f + expf(-x.z)); p.w = 1.f / (1.f + expf(-x.w));
@@ -151,6 +153,7 @@ __global__ void __launch_bounds__(256) k_decode_cls_v4(const __grid_constant__ D
 #endif
 #define DCB_STR(x) #x
 #define DCB_PRAGMA(n) _Pragma(DCB_STR(unroll n))
+template <typename T>
 __global__ void __launch_bounds__(256, DCB_MINB) k_decode_cls_best_v4(const __grid_constant__ DecodeArgs d, float* __restrict__ out,
                                                                int2* __restrict__ best) {
     const int A = d.grid.off[YCR_MAX_LEVELS];
@@ -165,13 +168,13 @@ __global__ void __launch_bounds__(256, DCB_MINB) k_decode_cls_best_v4(const __gr
     const int al = an - d.grid.off[l];
     const int R = d.R, nc = d.nc;
     const int CH = 4 + nc + 3 * R;
-    const float* fc = d.feats[l] + (int64_t)b * (R + nc) * hw + (int64_t)R * hw + al;
+    const T* fc = reinterpret_cast<const T*>(d.feats[l]) + (int64_t)b * (R + nc) * hw + (int64_t)R * hw + al;
     float* o = out + (int64_t)b * CH * A + an;
     float bs[4] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
     int bc[4] = {0, 0, 0, 0};
 DCB_PRAGMA(DCB_UNROLL)
     for (int c = 0; c < nc; ++c) {
-        const float4 x = __ldcs(reinterpret_cast<const float4*>(fc + (int64_t)c * hw));
+        const float4 x = YcrType<T>::ld4cs(fc + (int64_t)c * hw);
         float4 p;
         p.x = 1.f / (1.f + expf(-x.x)); p.y = 1.f / (1.f + expf(-x.y));
         p.z = 1.f / (1.f + expf(-x.z)); p.w = 1.f / (1.f + expf(-x.w));
@@ -186,12 +189,19 @@ DCB_PRAGMA(DCB_UNROLL)
     reinterpret_cast<int4*>(bo)[1] = make_int4(__float_as_int(bs[2]), bc[2], __float_as_int(bs[3]), bc[3]);
 }
 
-int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int nc, int R, float* allpred, int2* best,
+template <typename T>
+static void launch_decode_v4(const DecodeArgs& d, dim3 g, dim3 gc, float* allpred, int2* best, cudaStream_t st) {
+    k_decode_rays_v4<T><<<g, 256, 0, st>>>(d, allpred);
+    if (best && reinterpret_cast<uintptr_t>(best) % 16 == 0) k_decode_cls_best_v4<T><<<g, 256, 0, st>>>(d, allpred, best);
+    else k_decode_cls_v4<T><<<gc, 256, 0, st>>>(d, allpred);
+}
+
+int launch_decode(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, float* allpred, int2* best,
                   cudaStream_t st) {
     DecodeArgs d{};
     d.grid = make_grid_dev(grid);
     for (int l = 0; l < grid->n_levels; ++l) d.feats[l] = feats[l];
-    d.B = B; d.nc = nc; d.R = R;
+    d.B = B; d.nc = nc; d.R = R; d.dtype = dtype;
     for (int i = 0; i < R; ++i) {
         // angles = arange(0,360,360//R)/180.*pi in fp32 (nn/modules/head.py:466), then sin/cos
         const float deg = (float)(i * (360 / R));
@@ -200,16 +210,17 @@ int launch_decode(const ycr_grid_t* grid, const float* const* feats, int B, int 
         d.cs[R + i] = (float)sin((double)ang);
     }
     const int A = d.grid.off[YCR_MAX_LEVELS];
+    const uintptr_t align = 4 * ycr_dtype_size(dtype);
     bool vec = (reinterpret_cast<uintptr_t>(allpred) % 16 == 0);
     for (int l = 0; l < grid->n_levels; ++l)
-        vec = vec && (grid->w[l] % 4 == 0) && (reinterpret_cast<uintptr_t>(feats[l]) % 16 == 0);
+        vec = vec && (grid->w[l] % 4 == 0) && (reinterpret_cast<uintptr_t>(feats[l]) % align == 0);
     if (vec) {
         dim3 g((A / 4 + 255) / 256, B);
         dim3 gc((A / 4 + 255) / 256, (nc + 7) / 8, B);
         YcrProfScope ps(YCR_T_DECODE, st);
-        k_decode_rays_v4<<<g, 256, 0, st>>>(d, allpred);
-        if (best && reinterpret_cast<uintptr_t>(best) % 16 == 0) k_decode_cls_best_v4<<<g, 256, 0, st>>>(d, allpred, best);
-        else k_decode_cls_v4<<<gc, 256, 0, st>>>(d, allpred);
+        if (dtype == YCR_F16) launch_decode_v4<__half>(d, g, gc, allpred, best, st);
+        else if (dtype == YCR_BF16) launch_decode_v4<__nv_bfloat16>(d, g, gc, allpred, best, st);
+        else launch_decode_v4<float>(d, g, gc, allpred, best, st);
     } else {
         dim3 g((A + 255) / 256, B);
         YcrProfScope ps(YCR_T_DECODE, st);

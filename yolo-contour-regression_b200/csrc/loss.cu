@@ -9,8 +9,8 @@
 // One thread per anchor, looping over the channel dimension: every global access of a warp is a
 // contiguous 128-byte line of the NCHW feature map (a_local is the fastest dimension).
 __global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
-                                                       const float* f0, const float* f1, const float* f2, const float* f3,
-                                                       float* g0, float* g1, float* g2, float* g3, float cls_gain) {
+                                                       const void* f0, const void* f1, const void* f2, const void* f3,
+                                                       void* g0, void* g1, void* g2, void* g3, float cls_gain) {
     pdl_enter();
     __shared__ float s_red[K5_NT / 32];
     const int A = a.grid.off[YCR_MAX_LEVELS];
@@ -23,8 +23,9 @@ __global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ A
 #pragma unroll
         for (int k = 1; k < YCR_MAX_LEVELS; ++k)
             if (k < a.grid.n_levels && an >= a.grid.off[k]) l = k;
-        const float* f = (l == 0) ? f0 : (l == 1) ? f1 : (l == 2) ? f2 : f3;
-        float* g = (l == 0) ? g0 : (l == 1) ? g1 : (l == 2) ? g2 : g3;
+        const void* f = (l == 0) ? f0 : (l == 1) ? f1 : (l == 2) ? f2 : f3;
+        void* g = (l == 0) ? g0 : (l == 1) ? g1 : (l == 2) ? g2 : g3;
+        const int dt = a.dtype;
         const int hw = a.grid.h[l] * a.grid.w[l];
         const int al = an - a.grid.off[l];
         const int64_t base = (int64_t)b * (R + nc) * hw + al;
@@ -36,30 +37,24 @@ __global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ A
             const int gi = ws.pos_g[(int64_t)b * ws.pos_cap + row];
             int64_t lab = (int64_t)a.gt.labels[(int64_t)(b * a.gt.G + gi) * a.gt.labels_stride];
             label = (int)(lab < 0 ? 0 : lab);
-            tnorm = ws.pos_norm[(int64_t)b * ws.pos_cap + row];
+            tnorm = ycr_round_to(ws.pos_norm[(int64_t)b * ws.pos_cap + row], dt);   // target_scores.to(dtype), utils/loss.py:867
             pg = ws.pos_grad + ((int64_t)b * ws.pos_cap + row) * R;
         }
         const float gscale = cls_gain * (float)a.gt.B / ws.tss[0];
         if (g) {
-            if (pg) {
-                for (int i = 0; i < R; ++i) g[base + (int64_t)i * hw] = pg[i];
-            } else {
-#pragma unroll 4
-                for (int i = 0; i < R; ++i) g[base + (int64_t)i * hw] = 0.f;
-            }
+            for (int i = 0; i < R; ++i) ycr_st(g, base + (int64_t)i * hw, pg ? pg[i] : 0.f, dt);
         }
-        const float* fc = f + base + (int64_t)R * hw;
-        float* gc = g ? g + base + (int64_t)R * hw : nullptr;
+        const int64_t cbase = base + (int64_t)R * hw;
 #pragma unroll 4
         for (int c = 0; c < nc; ++c) {
-            const float x = fc[(int64_t)c * hw];
+            const float x = ycr_ld(f, cbase + (int64_t)c * hw, dt);
             const float t = (c == label) ? tnorm : 0.f;
             const float e = __expf(-fabsf(x));
             acc += fmaxf(x, 0.f) - x * t + log1pf(e);
-            if (gc) {
+            if (g) {
                 const float r = __fdividef(1.f, 1.f + e);
                 const float sig = (x >= 0.f) ? r : e * r;
-                gc[(int64_t)c * hw] = (sig - t) * gscale;
+                ycr_st(g, cbase + (int64_t)c * hw, (sig - t) * gscale, dt);
             }
         }
     }
@@ -90,9 +85,10 @@ __device__ __forceinline__ float bce_term(float x, float t, float gscale, float&
     return fmaxf(x, 0.f) - x * t + __logf(1.f + e);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(K5_NT, K5_MINB) k_loss_stream_v4(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
-                                                          const float* f0, const float* f1, const float* f2, const float* f3,
-                                                          float* g0, float* g1, float* g2, float* g3, float cls_gain) {
+                                                          const T* f0, const T* f1, const T* f2, const T* f3,
+                                                          T* g0, T* g1, T* g2, T* g3, float cls_gain) {
     pdl_enter();
     __shared__ float s_red[K5_NT / 32];
     const int A = a.grid.off[YCR_MAX_LEVELS];
@@ -105,8 +101,8 @@ __global__ void __launch_bounds__(K5_NT, K5_MINB) k_loss_stream_v4(const __grid_
 #pragma unroll
         for (int k = 1; k < YCR_MAX_LEVELS; ++k)
             if (k < a.grid.n_levels && an >= a.grid.off[k]) l = k;
-        const float* f = (l == 0) ? f0 : (l == 1) ? f1 : (l == 2) ? f2 : f3;
-        float* g = (l == 0) ? g0 : (l == 1) ? g1 : (l == 2) ? g2 : g3;
+        const T* f = (l == 0) ? f0 : (l == 1) ? f1 : (l == 2) ? f2 : f3;
+        T* g = (l == 0) ? g0 : (l == 1) ? g1 : (l == 2) ? g2 : g3;
         const int hw = a.grid.h[l] * a.grid.w[l];
         const int al = an - a.grid.off[l];
         const int64_t base = (int64_t)b * (R + nc) * hw + al;
@@ -123,7 +119,7 @@ __global__ void __launch_bounds__(K5_NT, K5_MINB) k_loss_stream_v4(const __grid_
                     const int gi = ws.pos_g[(int64_t)b * ws.pos_cap + row[k]];
                     const int64_t lab = (int64_t)a.gt.labels[(int64_t)(b * a.gt.G + gi) * a.gt.labels_stride];
                     label[k] = (int)(lab < 0 ? 0 : lab);
-                    tn[k] = ws.pos_norm[(int64_t)b * ws.pos_cap + row[k]];
+                    tn[k] = ycr_round_to(ws.pos_norm[(int64_t)b * ws.pos_cap + row[k]], YcrType<T>::code);   // target_scores.to(dtype)
                     pg[k] = ws.pos_grad + ((int64_t)b * ws.pos_cap + row[k]) * R;
                 }
             }
@@ -135,28 +131,28 @@ __global__ void __launch_bounds__(K5_NT, K5_MINB) k_loss_stream_v4(const __grid_
                     float4 v;
                     v.x = pg[0] ? pg[0][i] : 0.f; v.y = pg[1] ? pg[1][i] : 0.f;
                     v.z = pg[2] ? pg[2][i] : 0.f; v.w = pg[3] ? pg[3][i] : 0.f;
-                    __stcs(reinterpret_cast<float4*>(g + base + (int64_t)i * hw), v);
+                    YcrType<T>::st4cs(g + base + (int64_t)i * hw, v);
                 }
             } else {
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-                for (int i = 0; i < R; ++i) __stcs(reinterpret_cast<float4*>(g + base + (int64_t)i * hw), z);
+                for (int i = 0; i < R; ++i) YcrType<T>::st4cs(g + base + (int64_t)i * hw, z);
             }
         }
-        const float* fc = f + base + (int64_t)R * hw;
-        float* gc = g ? g + base + (int64_t)R * hw : nullptr;
+        const T* fc = f + base + (int64_t)R * hw;
+        T* gc = g ? g + base + (int64_t)R * hw : nullptr;
 #ifndef K5_UNROLL
 #define K5_UNROLL 4
 #endif
 YCR_PRAGMA_UNROLL(K5_UNROLL)
         for (int c = 0; c < nc; ++c) {
-            const float4 x = __ldcs(reinterpret_cast<const float4*>(fc + (int64_t)c * hw));
+            const float4 x = YcrType<T>::ld4cs(fc + (int64_t)c * hw);
             float4 gr;
             acc += bce_term(x.x, (c == label[0]) ? tn[0] : 0.f, gscale, gr.x);
             acc += bce_term(x.y, (c == label[1]) ? tn[1] : 0.f, gscale, gr.y);
             acc += bce_term(x.z, (c == label[2]) ? tn[2] : 0.f, gscale, gr.z);
             acc += bce_term(x.w, (c == label[3]) ? tn[3] : 0.f, gscale, gr.w);
-            if (gc) __stcs(reinterpret_cast<float4*>(gc + (int64_t)c * hw), gr);
+            if (gc) YcrType<T>::st4cs(gc + (int64_t)c * hw, gr);
         }
     }
     acc = warp_sum(acc);
@@ -206,25 +202,37 @@ __global__ void __launch_bounds__(1024) k_loss_finalize(AssignWs ws, int B, int 
     }
 }
 
-int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* const* feats, float* const* grads,
+template <typename T>
+static cudaError_t launch_stream_v4(const AssignArgs& a, const AssignWs& ws, const void* const* f, void* const* g, dim3 grid,
+                                    float cls_gain, cudaStream_t st) {
+    return ycr_launch(k_loss_stream_v4<T>, grid, dim3(K5_NT), 0, st, a, ws, reinterpret_cast<const T*>(f[0]),
+                      reinterpret_cast<const T*>(f[1]), reinterpret_cast<const T*>(f[2]), reinterpret_cast<const T*>(f[3]),
+                      reinterpret_cast<T*>(g[0]), reinterpret_cast<T*>(g[1]), reinterpret_cast<T*>(g[2]), reinterpret_cast<T*>(g[3]),
+                      cls_gain);
+}
+
+int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const void* const* feats, void* const* grads,
                        const ycr_loss_cfg_t& lcfg, float* loss_out, cudaStream_t st) {
     const int B = a.gt.B;
     const int A = a.grid.off[YCR_MAX_LEVELS];
-    const float* f[4] = {nullptr, nullptr, nullptr, nullptr};
-    float* g[4] = {nullptr, nullptr, nullptr, nullptr};
+    const void* f[4] = {nullptr, nullptr, nullptr, nullptr};
+    void* g[4] = {nullptr, nullptr, nullptr, nullptr};
+    const uintptr_t align = 4 * ycr_dtype_size(a.dtype);   // four elements per access
     bool vec = true;
     for (int l = 0; l < a.grid.n_levels; ++l) {
         f[l] = feats[l];
         g[l] = grads ? grads[l] : nullptr;
-        vec = vec && ((a.grid.h[l] * a.grid.w[l]) % 4 == 0) && (reinterpret_cast<uintptr_t>(f[l]) % 16 == 0) &&
-              (!g[l] || reinterpret_cast<uintptr_t>(g[l]) % 16 == 0);
+        vec = vec && ((a.grid.h[l] * a.grid.w[l]) % 4 == 0) && (reinterpret_cast<uintptr_t>(f[l]) % align == 0) &&
+              (!g[l] || reinterpret_cast<uintptr_t>(g[l]) % align == 0);
     }
     int nblk;
     if (vec) {
         dim3 grid((A / 4 + K5_NT - 1) / K5_NT, B);
         nblk = (int)(grid.x * grid.y);
         YcrProfScope ps(YCR_T_STREAM, st);
-        YCR_CUDA_CHECK(ycr_launch(k_loss_stream_v4, grid, dim3(K5_NT), 0, st, a, ws, f[0], f[1], f[2], f[3], g[0], g[1], g[2], g[3], lcfg.cls_gain));
+        if (a.dtype == YCR_F16) YCR_CUDA_CHECK(launch_stream_v4<__half>(a, ws, f, g, grid, lcfg.cls_gain, st));
+        else if (a.dtype == YCR_BF16) YCR_CUDA_CHECK(launch_stream_v4<__nv_bfloat16>(a, ws, f, g, grid, lcfg.cls_gain, st));
+        else YCR_CUDA_CHECK(launch_stream_v4<float>(a, ws, f, g, grid, lcfg.cls_gain, st));
     } else {
         dim3 grid((A + K5_NT - 1) / K5_NT, B);
         nblk = (int)(grid.x * grid.y);
@@ -240,7 +248,7 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* con
 // ------------------------------------------------------------------------------------------------
 // grad *= scale (device scalar); exits at once when the scalar is 1
 // ------------------------------------------------------------------------------------------------
-struct ScaleArgs { float* p[YCR_MAX_LEVELS]; int64_t n[YCR_MAX_LEVELS]; int n_levels; };
+struct ScaleArgs { void* p[YCR_MAX_LEVELS]; int64_t n[YCR_MAX_LEVELS]; int n_levels; int dtype; };
 
 __global__ void __launch_bounds__(256) k_scale(const ScaleArgs sa, const float* scale) {
     pdl_enter();
@@ -248,12 +256,14 @@ __global__ void __launch_bounds__(256) k_scale(const ScaleArgs sa, const float* 
     if (s == 1.f) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int l = 0; l < sa.n_levels; ++l)
-        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sa.n[l]; i += stride) sa.p[l][i] *= s;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sa.n[l]; i += stride)
+            ycr_st(sa.p[l], i, ycr_ld(sa.p[l], i, sa.dtype) * s, sa.dtype);
 }
 
-int launch_scale(float* const* p, const int64_t* n, int n_levels, const float* scale, cudaStream_t st) {
+int launch_scale(void* const* p, const int64_t* n, int n_levels, int dtype, const float* scale, cudaStream_t st) {
     ScaleArgs sa{};
     sa.n_levels = 0;
+    sa.dtype = dtype;
     for (int l = 0; l < n_levels && l < YCR_MAX_LEVELS; ++l)
         if (n[l] > 0) { sa.p[sa.n_levels] = p[l]; sa.n[sa.n_levels] = n[l]; ++sa.n_levels; }
     if (sa.n_levels == 0) return YCR_OK;

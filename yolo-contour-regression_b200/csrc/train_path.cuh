@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "polar_core.cuh"
+#include "dtype.cuh"
 
 // Everything the assignment stage leaves in the workspace.
 struct AssignWs {
@@ -53,6 +54,7 @@ struct AssignArgs {
     ycr_gt_t gt;
     ycr_assign_cfg_t cfg;
     PolarConst pc;
+    int dtype;   // YCR_F32 / YCR_F16 / YCR_BF16: element type behind pred.rays / pred.cls (fused loss: of the feature maps)
 };
 
 int launch_assign_core(const AssignArgs& a, const AssignWs& ws, int* n_pos_d, cudaStream_t st);
@@ -60,5 +62,5 @@ int launch_assign_dense(const AssignArgs& a, const AssignWs& ws, const ycr_assig
 int launch_positive_targets(const AssignArgs& a, const AssignWs& ws, float* gt_dist, float* centerness,
                             int pos_capacity, bool with_loss, const ycr_loss_cfg_t* lcfg,
                             cudaStream_t st);
-int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const float* const* feats, float* const* grads,
+int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const void* const* feats, void* const* grads,
                        const ycr_loss_cfg_t& lcfg, float* loss_out, cudaStream_t st);

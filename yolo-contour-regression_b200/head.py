@@ -16,7 +16,8 @@ from . import _lib as L
 def decode(feats, strides, nc: int, R: int = 36):
     """feats: list of (B, R+nc, H_l, W_l) -> allpred (B, 4+nc+3R, A), as distance2mask returns it."""
     L.require_cuda(*feats)
-    feats = [f if (f.dtype == torch.float32 and f.is_contiguous()) else f.float().contiguous() for f in feats]
+    dt = feats[0].dtype if feats[0].dtype in L.DTYPE_CODE else torch.float32   # fp16 / bf16 maps are read in place
+    feats = [f if (f.dtype == dt and f.is_contiguous()) else f.to(dt).contiguous() for f in feats]
     B = feats[0].shape[0]
     if feats[0].shape[1] != R + nc:
         raise ValueError(f"feature maps have {feats[0].shape[1]} channels, expected {R + nc}")
@@ -28,9 +29,9 @@ def decode(feats, strides, nc: int, R: int = 36):
     # this very object and no in-place operation has touched it since (version counter).
     best = torch.empty(B, A, 2, device=feats[0].device, dtype=torch.int32)
     cgrid = L.make_grid(shapes, [float(s) for s in strides])
-    rc = L.lib().ycr_decode_best(C.byref(cgrid), L.ptr_array(feats), B, nc, R, out.data_ptr(), best.data_ptr(),
-                                 L.stream_ptr(out.device))
-    L.check(rc, "ycr_decode_best")
+    rc = L.lib().ycr_decode_dt(C.byref(cgrid), L.ptr_array(feats), L.DTYPE_CODE[dt], B, nc, R, out.data_ptr(),
+                               best.data_ptr(), L.stream_ptr(out.device))
+    L.check(rc, "ycr_decode_dt")
     out._ycr_best_class = (best, out._version, nc)
     return out
 

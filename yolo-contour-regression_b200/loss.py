@@ -46,9 +46,11 @@ class _SegLossFn(torch.autograd.Function):
         ws = L.Workspace.get("seg_loss", nbytes, dev)
         fp = L.ptr_array(feats)
         gp = L.ptr_array(grads) if grads is not None else None
-        rc = lib.ycr_seg_loss_fwd_bwd(C.byref(cgrid), fp, gp, C.byref(gt), C.byref(crit.acfg), C.byref(crit.lcfg),
-                                      loss_out.data_ptr(), ws.data_ptr(), ws.numel(), cand_cap, L.stream_ptr(dev))
-        L.check(rc, "ycr_seg_loss_fwd_bwd")
+        dt = L.DTYPE_CODE[feats[0].dtype]
+        rc = lib.ycr_seg_loss_fwd_bwd_dt(C.byref(cgrid), fp, gp, dt, C.byref(gt), C.byref(crit.acfg), C.byref(crit.lcfg),
+                                         loss_out.data_ptr(), ws.data_ptr(), ws.numel(), cand_cap, L.stream_ptr(dev))
+        L.check(rc, "ycr_seg_loss_fwd_bwd_dt")
+        ctx.dt = dt
         ctx.grads = grads
         ctx.scaled = False
         ctx.cgrid = cgrid
@@ -70,9 +72,9 @@ class _SegLossFn(torch.autograd.Function):
             raise RuntimeError("v8SegmentationLoss: backward through the same loss twice is not supported "
                                "(the gradient maps are produced once, by the forward kernel)")
         ctx.scaled = True
-        rc = L.lib().ycr_scale_grads(C.byref(ctx.cgrid), ctx.B, ctx.channels, L.ptr_array(grads), g.data_ptr(),
-                                     L.stream_ptr(dev))
-        L.check(rc, "ycr_scale_grads")
+        rc = L.lib().ycr_scale_grads_dt(C.byref(ctx.cgrid), ctx.B, ctx.channels, L.ptr_array(grads), ctx.dt, g.data_ptr(),
+                                        L.stream_ptr(dev))
+        L.check(rc, "ycr_scale_grads_dt")
         return (None, None, None) + tuple(grads)
 
 
@@ -205,7 +207,9 @@ class v8SegmentationLoss:
     def __call__(self, preds, batch):
         feats, _, _ = preds if len(preds) == 3 else preds[1]  # utils/loss.py:812
         L.require_cuda(*feats)
-        feats = [f if (f.dtype == torch.float32 and f.is_contiguous()) else f.float().contiguous() for f in feats]
+        # fp32, fp16 and bf16 maps are read in place (autocast is the reference's default, engine/trainer.py:332)
+        dt = feats[0].dtype if feats[0].dtype in L.DTYPE_CODE else torch.float32
+        feats = [f if (f.dtype == dt and f.is_contiguous()) else f.to(dt).contiguous() for f in feats]
         B = feats[0].shape[0]
         if feats[0].shape[1] != self.rays + self.nc:
             raise ValueError(f"head emits {feats[0].shape[1]} channels, expected rays+nc = {self.rays + self.nc}")
