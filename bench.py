@@ -193,6 +193,65 @@ def bind_to_gpu_numa_node(gpu_index):
         pass
 
 
+def run_dp_step(cfg, dev, world, local, batch, steps):
+    """BASELINE configs[4]: the data-parallel training step around the path.  The Segment head of a yolov8x-sized neck
+    (cuDNN convolutions under autocast, as the reference trains) feeds the fused loss; with more than one rank the head
+    is wrapped in DistributedDataParallel, so the bucketed NCCL all-reduce of its 35 MB of gradients runs during the
+    backward pass, `loss *= world_size` as engine/trainer.py:365.  The step is timed with and without the all-reduce
+    (`no_sync`): the difference is the part of the collective the backward pass does not hide."""
+    import contextlib
+    from ycr_b200.head import Segment
+    from ycr_b200.loss import v8SegmentationLoss
+    B = cfg.batch
+    ch = (320, 640, 640)   # neck widths of yolov8x at the three head levels
+    torch.manual_seed(1234)
+    head = Segment(nc=cfg.nc, nm=cfg.rays, ch=ch).to(dev)
+    head.stride = torch.tensor(cfg.strides, dtype=torch.float32)
+    head.bias_init()
+    head.train()
+    model = head
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(head, device_ids=[local])
+    crit = v8SegmentationLoss(nc=cfg.nc, nm=cfg.rays, strides=cfg.strides, device=dev)
+    g = torch.Generator(device=dev).manual_seed(77 + local)
+    x = [torch.randn(B, c, h, w, device=dev, dtype=torch.float16, generator=g) * 0.5
+         for c, (h, w) in zip(ch, cfg.level_shapes)]
+    n_param = sum(p.numel() for p in head.parameters())
+
+    def step(sync=True):
+        model.zero_grad(set_to_none=True)
+        ctx = contextlib.nullcontext() if (sync or world == 1) else model.no_sync()
+        with ctx:
+            with torch.autocast("cuda", dtype=torch.float16):
+                feats, _, _ = model(x)
+            loss, items = crit((feats, 5, 2), batch)       # fp16 maps, read in place
+            if world > 1:
+                loss = loss * world
+            loss.backward()
+
+    def timed(sync):
+        for _ in range(3):
+            step(sync)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(sync)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    ms_sync = timed(True)
+    ms_nosync = timed(False) if world > 1 else ms_sync
+    del x, model, head
+    torch.cuda.empty_cache()
+    return ms_sync, ms_nosync, n_param
+
+
 def run_ours(args):
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback in the product)"
@@ -208,7 +267,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     use_dist = world > 1
-    if use_dist:   # (at N=1 the CPU baseline leg wants every host core)
+    if use_dist and not os.environ.get("YCR_NO_BIND"):   # (at N=1 the CPU baseline leg wants every host core)
         bind_to_gpu_numa_node(local)
     if use_dist:
         import torch.distributed as dist
@@ -281,6 +340,20 @@ def run_ours(args):
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    # the same steps with the GT rows already packed on the device (what round 1 timed): shows what the packing costs
+    crit._shapes = [tuple(f.shape[2:]) for f in feats_d]
+    packed, cap = crit.pack_targets(batch, B, (cfg.imgsz, cfg.imgsz))
+    torch.cuda.synchronize()
+    pp0, pp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pp0.record()
+    for _ in range(args.steps):
+        for f in feats_d:
+            f.grad = None
+        tot_pp, _ = crit.call_packed(feats_d, packed, cap)
+        tot_pp.backward()
+    pp1.record()
+    torch.cuda.synchronize()
+    ms_prepacked = pp0.elapsed_time(pp1) / args.steps
     sums = (C.c_float * 16)()
     counts = (C.c_int * 16)()
     L.check(lib.ycr_profile_end(sums, counts), "ycr_profile_end")
@@ -408,8 +481,12 @@ def run_ours(args):
     L.check(lib.ycr_profile_end(isums, icounts), "ycr_profile_end")
     kept = sum(d.shape[0] for d in dets) / ib
 
+    # ---- data-parallel training step (configs[4]), every rank ----
+    dp_steps = max(3, min(args.steps, 10))
+    ms_dp, ms_dp_nosync, dp_params = run_dp_step(cfg, dev, world, local, batch, dp_steps)
+
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([ms_total, ms_e2e, ms_inf, ms_res16, ms_e2e16], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, ms_e2e, ms_inf, ms_res16, ms_e2e16, ms_dp, ms_dp_nosync], device=dev, dtype=torch.float64)
     per_rank = None
     if use_dist:
         import torch.distributed as dist
@@ -418,7 +495,7 @@ def run_ours(args):
         per_rank = {"ms_per_step": [float(g[0]) / args.steps for g in gathered],
                     "e2e_ms_per_step": [float(g[1]) / e_steps for g in gathered]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_inf, ms_res16, ms_e2e16 = [float(x) for x in t.tolist()]
+    ms_total, ms_e2e, ms_inf, ms_res16, ms_e2e16, ms_dp, ms_dp_nosync = [float(x) for x in t.tolist()]
     if rank != 0:
         if use_dist:
             import torch.distributed as dist
@@ -471,6 +548,7 @@ def run_ours(args):
                           "bytes_per_image": bytes_img},
         "kernels_ms": kern,
         "host_issue_ms_per_step": host_issue_ms,
+        "ms_per_step_gt_prepacked": ms_prepacked,
         "loss_stream_hbm_frac": (stream_bytes / (kern["loss_stream"] * 1e-3) / 1e9 / peak) if "loss_stream" in kern else None,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": in_bytes + gt_rows_bytes,
                 "d2h_bytes_per_step": 4, "steps": e_steps},
@@ -481,6 +559,11 @@ def run_ours(args):
                         "value": world * B / (ms_res16 / h_steps / 1e3), "ms_per_step": ms_res16 / h_steps,
                         "e2e": {"value": world * B / (ms_e2e16 / e_steps / 1e3), "unit": "images/s",
                                 "h2d_bytes_per_step": in_bytes // 2 + gt_rows_bytes, "d2h_bytes_per_step": 4}},
+        "dp_step": {"workload": f"configs[4]: Segment head of a yolov8x neck (cuDNN, fp16 autocast) + fused loss + backward, "
+                                f"batch {B}/GPU, DistributedDataParallel over {world} rank(s), loss *= world_size",
+                    "value": world * B / (ms_dp / 1e3), "unit": "images/s", "ms_per_step": ms_dp,
+                    "ms_per_step_no_allreduce": ms_dp_nosync, "allreduce_exposed_ms": max(ms_dp - ms_dp_nosync, 0.0),
+                    "allreduce_bytes": dp_params * 4, "collective": "NCCL all-reduce of the head gradients (DDP buckets)"},
         "gpu_launches": 11 * args.steps,
         "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
                   "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",

@@ -193,6 +193,22 @@ int ycr_pack_targets(const float* targets, int64_t row_stride, int N, int B, int
 int ycr_pack_targets_split(const float* head, int64_t head_stride, const float* segments, int64_t seg_stride, int N, int B, int G,
                            float img_w, float img_h, float* out_packed, void* stream);
 
+/* Host-side half of GT packing (everything in host memory, no CUDA call): lays the rows of a collated batch out in
+ * one staging buffer - N x 6 header floats [image index, class, x, y, w, h] followed by N x 720 contour floats, the
+ * layout ycr_pack_targets_split takes after one host-to-device copy - and returns G = the largest number of boxes
+ * of one image (utils/loss.py:224-226) and the candidate bound.  batch['segments'] arrives as a list of per-image
+ * tensors: seg_ptrs_h[k] holds seg_rows_h[k] rows of 720 floats.  Behind the rows it writes the int32 table
+ * row_of[b*G + slot] (row index or -1 for padding) that ycr_pack_targets_mapped takes.  staging_h needs
+ * N * 726 floats + B * G ints, G <= N (pinned, so that the copy is asynchronous). */
+int ycr_stage_targets_h(const float* batch_idx_h, const float* cls_h, const float* bboxes_h, const float* const* seg_ptrs_h,
+                        const int* seg_rows_h, int n_seg_tensors, int N, int B, const ycr_grid_t* grid, float img_w, float img_h,
+                        float* staging_h, int* G_out, int64_t* cand_bound_out);
+
+/* GT packing from staged rows and the row table of ycr_stage_targets_h: one block per padded (image, slot) row, every
+ * element of out_packed (B, G, 725) is written (no memset). */
+int ycr_pack_targets_mapped(const float* head, int64_t head_stride, const float* segments, int64_t seg_stride, const int* row_of,
+                            int B, int G, float img_w, float img_h, float* out_packed, void* stream);
+
 /* Contour resampling, replaces ops.resample_segments (utils/ops.py:676-693; n = 360 at
  * utils/instance.py:202): S open polygons stored back to back in pts (total,2); polygon s owns rows
  * offsets[s] .. offsets[s+1]-1.  Each is closed and linearly resampled to n_out points ->

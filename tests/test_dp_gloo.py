@@ -47,6 +47,13 @@ def _worker(rank, world, port, q):
         # image independence: per-rank assignment == slice of the full-batch assignment
         assert torch.equal(r["assign"]["target_gt_idx"], ref["assign"]["target_gt_idx"][lo:hi])
         assert torch.equal(r["assign"]["fg_mask"], ref["assign"]["fg_mask"][lo:hi])
+        # global-normaliser mode: every rank's rescaled loss numerators add up to the full-batch loss
+        tss_local = torch.tensor(max(float(local), 1.0))
+        tot, items = dp.rescale_to_global_norm(r["loss"] / (hi - lo), r["loss_items"], tss_local)
+        both = items.clone()
+        dist.all_reduce(both)
+        if float(ref["assign"]["target_scores"].sum()) >= 1.0 and float(local) >= 1.0:
+            assert float((both - ref["loss_items"]).abs().max()) <= 2e-5 * float(ref["loss_items"].abs().max())
         ms = dp.max_over_ranks([10.0 + rank, 5.0 - rank])
         assert ms == [10.0 + world - 1, 5.0]
         assert float(dp.scale_loss_for_ddp(torch.tensor(2.0), world)) == 2.0 * world

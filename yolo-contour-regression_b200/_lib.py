@@ -86,6 +86,11 @@ EXPORTS = {
     "ycr_pack_targets_split": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_float, C.c_void_p, C.c_void_p]),
     "ycr_candidate_bound_xywhn_h": (C.c_int64, [C.POINTER(Grid), C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_float]),
+    "ycr_stage_targets_h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int,
+                                      C.c_int, C.c_int, C.POINTER(Grid), C.c_float, C.c_float, C.c_void_p,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "ycr_pack_targets_mapped": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                          C.c_float, C.c_void_p, C.c_void_p]),
     "ycr_resample_segments": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ycr_bbox_loss_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
     "ycr_bbox_loss_fwd_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]),

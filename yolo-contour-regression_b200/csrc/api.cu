@@ -16,6 +16,7 @@ void ycr_set_error(const char* fmt, ...) {
 
 // ---- per-kernel event timing --------------------------------------------------------------------
 #include <vector>
+#include <algorithm>
 static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_ev;       // pool
 static std::vector<int> g_prof_tag;              // tag of pair k (events 2k, 2k+1)
@@ -55,6 +56,9 @@ int launch_rasterize(const float* rows, int64_t row_stride, int n, int R, int H,
 size_t mask_iou_workspace_bytes(int N, int M, int64_t n);
 int launch_mask_iou(const void* m1, int dt1, const void* m2, int dt2, int N, int M, int64_t n, float eps, float* iou,
                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+int launch_pack_targets_mapped(const float* head, int64_t hs, const float* seg, int64_t ss, const int* row_of, int B, int G,
+                               float img_w, float img_h, float* out, cudaStream_t st);
 
 static int check_common(const ycr_grid_t* grid, const ycr_assign_cfg_t* cfg, int B, int G) {
     if (!grid || !cfg) { ycr_set_error("null grid/cfg"); return YCR_E_ARG; }
@@ -161,6 +165,54 @@ int64_t ycr_candidate_bound_xywhn_h(const ycr_grid_t* grid, const float* xywhn_h
         }
     }
     return total;
+}
+
+int ycr_stage_targets_h(const float* batch_idx_h, const float* cls_h, const float* bboxes_h, const float* const* seg_ptrs_h,
+                        const int* seg_rows_h, int n_seg_tensors, int N, int B, const ycr_grid_t* grid, float img_w, float img_h,
+                        float* staging_h, int* G_out, int64_t* cand_bound_out) {
+    if (!batch_idx_h || !cls_h || !bboxes_h || !seg_ptrs_h || !seg_rows_h || !grid || !staging_h || !G_out || !cand_bound_out ||
+        N < 0 || B < 1) {
+        ycr_set_error("bad stage_targets arguments");
+        return YCR_E_ARG;
+    }
+    float* head = staging_h;
+    float* seg = staging_h + (size_t)N * 6;
+    int64_t rows = 0;
+    for (int k = 0; k < n_seg_tensors; ++k) {
+        if (seg_rows_h[k] < 0 || rows + seg_rows_h[k] > N) { ycr_set_error("segment rows do not add up to the %d boxes", N); return YCR_E_ARG; }
+        memcpy(seg + (size_t)rows * 2 * YCR_C, seg_ptrs_h[k], (size_t)seg_rows_h[k] * 2 * YCR_C * sizeof(float));
+        rows += seg_rows_h[k];
+    }
+    if (rows != N) { ycr_set_error("segment rows (%lld) do not match the %d boxes", (long long)rows, N); return YCR_E_ARG; }
+    std::vector<int> count((size_t)B, 0);
+    int G = 0;
+    for (int n = 0; n < N; ++n) {
+        float* h = head + (size_t)n * 6;
+        h[0] = batch_idx_h[n];
+        h[1] = cls_h[n];
+        h[2] = bboxes_h[4 * n]; h[3] = bboxes_h[4 * n + 1]; h[4] = bboxes_h[4 * n + 2]; h[5] = bboxes_h[4 * n + 3];
+        const int b = (int)batch_idx_h[n];
+        if (b >= 0 && b < B) { const int c = ++count[(size_t)b]; if (c > G) G = c; }
+    }
+    *G_out = G;
+    *cand_bound_out = ycr_candidate_bound_xywhn_h(grid, head + 2, 6, N, img_w, img_h);
+    // row of every (image, slot): slot = rank of the row among its image's rows, in row order (utils/loss.py:228-232)
+    int* row_of = reinterpret_cast<int*>(staging_h + (size_t)N * (6 + 2 * YCR_C));
+    for (size_t i = 0; i < (size_t)B * G; ++i) row_of[i] = -1;
+    std::fill(count.begin(), count.end(), 0);
+    for (int n = 0; n < N; ++n) {
+        const int b = (int)batch_idx_h[n];
+        if (b >= 0 && b < B) row_of[(size_t)b * G + count[(size_t)b]++] = n;
+    }
+    return YCR_OK;
+}
+
+int ycr_pack_targets_mapped(const float* head, int64_t head_stride, const float* segments, int64_t seg_stride, const int* row_of,
+                            int B, int G, float img_w, float img_h, float* out_packed, void* stream) {
+    if (!out_packed || (B * G > 0 && (!head || !segments || !row_of))) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (B < 1 || G < 0 || head_stride < 6 || seg_stride < 2 * YCR_C) { ycr_set_error("bad B/G/strides"); return YCR_E_ARG; }
+    return launch_pack_targets_mapped(head, head_stride, segments, seg_stride, row_of, B, G, img_w, img_h, out_packed,
+                                      reinterpret_cast<cudaStream_t>(stream));
 }
 
 size_t ycr_assign_workspace_bytes(const ycr_grid_t* grid, int B, int G, const ycr_assign_cfg_t* cfg, int64_t cand_capacity) {

@@ -310,6 +310,37 @@ __global__ void __launch_bounds__(128) k_pack_targets(const float* __restrict__ 
     for (int k = threadIdx.x; k < 2 * YCR_C; k += 128) row[5 + k] = sg[k] * ((k < YCR_C) ? img_w : img_h);
 }
 
+// The same with the row of every (image, slot) known (row_of[b*G+g], -1 = padding; the host-side staging computes it
+// while it copies the rows): one block per padded row, no memset, no rank scan.
+__global__ void __launch_bounds__(128) k_pack_targets_mapped(const float* __restrict__ head, int64_t hs, const float* __restrict__ seg,
+                                                             int64_t ss, const int* __restrict__ row_of, float img_w, float img_h,
+                                                             float* __restrict__ out) {
+    pdl_enter();
+    const int bg = blockIdx.x;
+    const int n = row_of[bg];
+    float* row = out + (int64_t)bg * (5 + 2 * YCR_C);
+    if (n < 0) {
+        for (int k = threadIdx.x; k < 5 + 2 * YCR_C; k += 128) row[k] = 0.f;
+        return;
+    }
+    const float* t = head + (int64_t)n * hs;
+    const float* sg = seg + (int64_t)n * ss;
+    if (threadIdx.x == 0) {
+        row[0] = t[1];
+        const float cx = t[2] * img_w, cy = t[3] * img_h, w = t[4] * img_w, h = t[5] * img_h;
+        row[1] = cx - w / 2; row[2] = cy - h / 2; row[3] = cx + w / 2; row[4] = cy + h / 2;
+    }
+    for (int k = threadIdx.x; k < 2 * YCR_C; k += 128) row[5 + k] = sg[k] * ((k < YCR_C) ? img_w : img_h);
+}
+
+int launch_pack_targets_mapped(const float* head, int64_t hs, const float* seg, int64_t ss, const int* row_of, int B, int G,
+                               float img_w, float img_h, float* out, cudaStream_t st) {
+    if (B * G == 0) return YCR_OK;
+    YCR_CUDA_CHECK(ycr_launch(k_pack_targets_mapped, dim3(B * G), dim3(128), 0, st, head, hs, seg, ss, row_of, img_w, img_h, out));
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
 int launch_pack_targets(const float* head, int64_t hs, const float* seg, int64_t ss, int N, int B, int G, float img_w, float img_h,
                         float* out, cudaStream_t st) {
     // the padded tensor must be zero where no row lands; the compact index array comes from the stream-ordered pool

@@ -52,3 +52,14 @@ def global_target_scores_sum(local_sum: torch.Tensor) -> torch.Tensor:
 def scale_loss_for_ddp(loss: torch.Tensor, world: int) -> torch.Tensor:
     """engine/trainer.py:365 — DDP averages gradients, the reference multiplies the loss back."""
     return loss * world if world > 1 else loss
+
+
+def rescale_to_global_norm(total: torch.Tensor, items: torch.Tensor, local_tss: torch.Tensor):
+    """Optional global-normaliser mode of v8SegmentationLoss: the reference normalises each rank's
+    loss by its LOCAL max(target_scores.sum(), 1) (utils/loss.py:866) and lets DDP average the gradients; with
+    `global_norm` every rank divides by the sum over ranks instead - one fp32 scalar all-reduce, and the loss (hence,
+    through autograd, every gradient) is rescaled by local / global.  `local_tss` is the clamped local normaliser
+    the kernels used (exact whenever every rank has a target-score sum >= 1)."""
+    glob = global_target_scores_sum(local_tss.detach().float()).clamp(min=1.0)
+    ratio = (local_tss.detach().float() / glob).to(total.dtype)
+    return total * ratio, items * ratio

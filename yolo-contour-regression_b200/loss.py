@@ -84,7 +84,7 @@ class v8SegmentationLoss:
     `__call__(preds, batch)` -> `(loss.sum() * batch_size  [with grad], loss.detach() (2,))`, where
     loss = [box_gain * polar_iou_loss, cls_gain * bce] — identical to the reference's return."""
 
-    def __init__(self, model=None, *, nc=None, nm=36, strides=None, box=7.5, cls=0.5, device=None):
+    def __init__(self, model=None, *, nc=None, nm=36, strides=None, box=7.5, cls=0.5, device=None, global_norm=False):
         if model is not None:
             device = next(model.parameters()).device
             h = model.args
@@ -105,6 +105,8 @@ class v8SegmentationLoss:
             self.reg_max = 16
             self.overlap = True
         self.device = torch.device(device)
+        # False = the reference's DDP semantics (local normaliser); True = one scalar all-reduce per step (dp.py)
+        self.global_norm = bool(global_norm)
         self.stride_list = [float(s) for s in (self.stride.tolist() if torch.is_tensor(self.stride) else self.stride)]
         self.use_dfl = self.reg_max > 1
         self.assigner = TaskAlignedAssigner(topk=10, num_classes=self.nc, alpha=0.5, beta=4.0)  # utils/loss.py:210
@@ -114,18 +116,22 @@ class v8SegmentationLoss:
         self.lcfg = L.LossCfg(float(box), float(cls))
 
     # -- GT packing: utils/loss.py:834-844 + preprocess utils/loss.py:215-239 ----------------------
-    def _staging(self, n_rows):
-        """Pinned host buffer for n_rows GT rows: 6 header floats + 720 contour floats per row, header block first.
-        Waits until the copy that last read the buffer has finished."""
-        ev = getattr(self, "_stage_ev", None)
-        if ev is not None:
-            ev.synchronize()
-            self._stage_ev = None
-        buf = getattr(self, "_stage_buf", None)
-        if buf is None or buf.numel() < n_rows * 726:
-            buf = torch.empty(max(n_rows, 64) * 726, dtype=torch.float32).pin_memory()
-            self._stage_buf = buf
-        return buf[:n_rows * 726]
+    def _staging(self, n_rows, extra=0):
+        """One of two pinned host buffers for n_rows GT rows (6 header floats + 720 contour floats per row, header
+        block first), used in turn: the host only waits for the copy that read THIS buffer two steps ago."""
+        if getattr(self, "_stage_bufs", None) is None:
+            self._stage_bufs = [None, None]
+            self._stage_evs = [None, None]
+            self._stage_turn = 0
+        k = self._stage_turn = 1 - self._stage_turn
+        if self._stage_evs[k] is not None:
+            self._stage_evs[k].synchronize()
+            self._stage_evs[k] = None
+        buf = self._stage_bufs[k]
+        need = n_rows * 726 + extra
+        if buf is None or buf.numel() < need:
+            buf = self._stage_bufs[k] = torch.empty(max(need, 64 * 726), dtype=torch.float32).pin_memory()
+        return buf[:need]
 
     @property
     def last_gt_copy_event(self):
@@ -149,20 +155,36 @@ class v8SegmentationLoss:
         cgrid = L.make_grid(self._shapes, self.stride_list)
         seg_list = list(segs) if isinstance(segs, (list, tuple)) else [segs]
         on_host = all(t.device.type == "cpu" for t in seg_list) and bi.device.type == "cpu"
+        mapped = False
         if on_host:
-            stage = self._staging(N)
-            head = stage[:N * 6].view(N, 6)
-            seg = stage[N * 6:].view(N, 720)
-            srcs = [t.reshape(-1, 720) for t in seg_list]
-            if all(t.dtype == torch.float32 for t in srcs):
-                torch.cat(srcs, 0, out=seg)
+            stage = self._staging(N, batch_size * N)   # rows + the (image, slot) -> row table (at most B * N ints)
+            cls_t, box_t = batch["cls"].view(-1), batch["bboxes"].view(-1, 4)
+            plain = (bi.dtype == torch.float32 and cls_t.dtype == torch.float32 and box_t.dtype == torch.float32 and
+                     box_t.is_contiguous() and all(t.dtype == torch.float32 and t.is_contiguous() for t in seg_list))
+            if plain:
+                # one C call: memcpy of every image's contours into the pinned buffer, the header columns, G and the
+                # candidate bound (the torch ops this replaces cost more host time than the kernels take)
+                nt = len(seg_list)
+                ptrs = (C.c_void_p * nt)(*[t.data_ptr() for t in seg_list])
+                nrow = (C.c_int * nt)(*[t.numel() // 720 for t in seg_list])
+                g_out, cap_out = C.c_int(0), C.c_int64(0)
+                rc = lib.ycr_stage_targets_h(bi.data_ptr(), cls_t.data_ptr(), box_t.data_ptr(), ptrs, nrow, nt, N, batch_size,
+                                             C.byref(cgrid), w, h, stage.data_ptr(), C.byref(g_out), C.byref(cap_out))
+                if rc != 0:   # malformed rows: the reference re-wraps these as TypeError (utils/loss.py:850-856)
+                    raise RuntimeError(lib.ycr_last_error().decode())
+                G, cap = int(g_out.value), int(cap_out.value) + 64
+                mapped = True
+                stage = stage[:N * 726 + batch_size * G]
             else:
-                seg.copy_(torch.cat(srcs, 0))
-            head[:, 0] = bi
-            head[:, 1] = batch["cls"].view(-1)
-            head[:, 2:6] = batch["bboxes"].view(-1, 4)
-            G = int(torch.bincount(bi.long(), minlength=batch_size).max())
-            cap = int(lib.ycr_candidate_bound_xywhn_h(C.byref(cgrid), head.data_ptr() + 8, 6, N, w, h)) + 64
+                stage = stage[:N * 726]
+                head = stage[:N * 6].view(N, 6)
+                seg = stage[N * 6:].view(N, 720)
+                seg.copy_(torch.cat([t.reshape(-1, 720) for t in seg_list], 0))
+                head[:, 0] = bi
+                head[:, 1] = cls_t
+                head[:, 2:6] = box_t
+                G = int(torch.bincount(bi.long(), minlength=batch_size).max())
+                cap = int(lib.ycr_candidate_bound_xywhn_h(C.byref(cgrid), head.data_ptr() + 8, 6, N, w, h)) + 64
             # The copy goes on its own stream into one of two persistent device buffers: the host runs ahead of the
             # device, so the rows of step k+1 cross the bus while the kernels of step k still run.  The compute
             # stream waits for the copy; the copy waits until the kernel that last read this buffer has finished.
@@ -184,6 +206,7 @@ class v8SegmentationLoss:
                 rows.copy_(stage, non_blocking=True)
             self._stage_ev = torch.cuda.Event()
             self._stage_ev.record(cs)
+            self._stage_evs[self._stage_turn] = self._stage_ev
             cur.wait_event(self._stage_ev)
             self._rows_slot = k
         else:
@@ -195,9 +218,14 @@ class v8SegmentationLoss:
             cap = int(lib.ycr_candidate_bound_xywhn_h(C.byref(cgrid), bb_h.data_ptr(), 4, N, w, h)) + 64
             rows = torch.cat((head.reshape(-1), seg.reshape(-1)))
         out = torch.empty(batch_size, G, 5 + 720, device=dev)
-        rc = lib.ycr_pack_targets_split(rows.data_ptr(), 6, rows.data_ptr() + N * 6 * 4, 720, N, batch_size, G, w, h,
-                                        out.data_ptr(), L.stream_ptr(dev))
-        L.check(rc, "ycr_pack_targets_split")
+        if mapped:
+            rc = lib.ycr_pack_targets_mapped(rows.data_ptr(), 6, rows.data_ptr() + N * 6 * 4, 720,
+                                             rows.data_ptr() + N * 726 * 4, batch_size, G, w, h, out.data_ptr(),
+                                             L.stream_ptr(dev))
+        else:
+            rc = lib.ycr_pack_targets_split(rows.data_ptr(), 6, rows.data_ptr() + N * 6 * 4, 720, N, batch_size, G, w, h,
+                                            out.data_ptr(), L.stream_ptr(dev))
+        L.check(rc, "ycr_pack_targets")
         if on_host:   # the staged rows may be overwritten once this kernel has read them
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
@@ -225,7 +253,11 @@ class v8SegmentationLoss:
         gt, keep = gt_struct(gt_labels, gt_boxes, gt_coor, None)
         total, out = _SegLossFn.apply(self, gt, cap, *feats)
         del keep
-        return total, out[1:3].detach()
+        items = out[1:3].detach()
+        if self.global_norm:
+            from .dp import rescale_to_global_norm
+            total, items = rescale_to_global_norm(total, items, out[3])
+        return total, items
 
     def call_packed(self, feats, packed, cand_cap):
         """Extension: same as __call__ with GTs already packed on the device ((B,G,725), px)."""
