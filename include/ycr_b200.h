@@ -255,6 +255,13 @@ typedef struct {
     int compact_rows;   /* 0: image b's rows start at out_rows[b*max_det]; 1: rows of all images back to back
                          * (image b starts at row sum(out_counts[0..b-1])), so the host can split one tensor */
     const void* best_class; /* optional: what ycr_decode_best wrote for THIS prediction tensor, else NULL */
+    /* optional: the head feature maps THIS prediction tensor was decoded from (ycr_decode*, same grid, element type
+     * feats_dtype) - the kept rows are then recomputed from the R ray values of their anchor instead of being
+     * collected element by element from the channel-major prediction (a sector per element); NULL entries = off */
+    const void* feats[YCR_MAX_LEVELS];
+    const ycr_grid_t* grid;
+    int feats_dtype;
+    int rays;
 } ycr_nms_cfg_t;
 
 size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* cfg);

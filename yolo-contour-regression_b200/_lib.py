@@ -56,7 +56,8 @@ class NmsCfg(C.Structure):
     _fields_ = [("conf_thres", C.c_float), ("iou_thres", C.c_float), ("agnostic", C.c_int),
                 ("multi_label", C.c_int), ("max_det", C.c_int), ("nc", C.c_int), ("max_nms", C.c_int),
                 ("max_wh", C.c_float), ("classes", C.c_void_p), ("n_classes", C.c_int), ("compact_rows", C.c_int),
-                ("best_class", C.c_void_p)]
+                ("best_class", C.c_void_p), ("feats", C.c_void_p * MAX_LEVELS), ("grid", C.POINTER(Grid)),
+                ("feats_dtype", C.c_int), ("rays", C.c_int)]
 
 
 EXPORTS = {

@@ -336,6 +336,25 @@ __device__ void bitonic_sort(unsigned long long* d, int npow2) {
     }
 }
 
+// The same network with one thread per compare-exchange PAIR, run by the first `nthr` threads of the block only
+// (a multiple of 32; they meet at named barrier 1, the other warps go straight to the block barrier behind the
+// sort): for the few hundred candidates of a typical image most of a 1024-thread block would only add barrier cost.
+__device__ void bitonic_sort_pairs(unsigned long long* d, int npow2, int nthr) {
+    const int half = npow2 >> 1;
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < half; t += nthr) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int ixj = i | j;
+                const unsigned long long x = d[i], y = d[ixj];
+                const bool up = ((i & k) == 0);
+                if ((x > y) == up) { d[i] = y; d[ixj] = x; }
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+        }
+    }
+}
+
 #define NMS_SORT_SMEM 4096
 #define NMS_PRESEL_MIN 32768   // above this many candidates the top max_nms are selected before sorting
 
@@ -422,7 +441,9 @@ __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pre
         if (np2 <= NMS_SORT_SMEM) {
             for (int i = threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = (i < n) ? keys[i] : 0xFFFFFFFFFFFFFFFFull;
             __syncthreads();
-            bitonic_sort(s_keys, np2);
+            const int nthr = min((int)blockDim.x, max(32, np2 >> 1));   // (block-uniform: n is)
+            if ((int)threadIdx.x < nthr) bitonic_sort_pairs(s_keys, np2, nthr);
+            __syncthreads();
             for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = s_keys[i];
         } else {
             for (int i = n + threadIdx.x; i < np2; i += blockDim.x) keys[i] = 0xFFFFFFFFFFFFFFFFull;
@@ -451,6 +472,9 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
     const float w = fmaxf(0.f, fminf(a.z, b.z) - fmaxf(a.x, b.x));
     const float h = fmaxf(0.f, fminf(a.w, b.w) - fmaxf(a.y, b.y));
     const float inter = __fmul_rn(w, h);
+    // disjoint boxes (most pairs): 0 / union is 0 or NaN, never above a threshold >= 0 - and a zero numerator sends
+    // the IEEE division to its slow path
+    if (!(inter > 0.f)) return false;
     const float area_b = __fmul_rn(b.z - b.x, b.w - b.y);
     const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
     return iou > thr;
@@ -510,7 +534,7 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
                 const float w = fmaxf(0.f, fminf(bk.z, bi.z) - fmaxf(bk.x, bi.x));
                 const float h = fmaxf(0.f, fminf(bk.w, bi.w) - fmaxf(bk.y, bi.y));
                 const float inter = __fmul_rn(w, h);
-                dead = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, ai), inter)) > thr;
+                dead = (inter > 0.f) && (__fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, ai), inter)) > thr);
             }
             if (dead) atomicOr(&s_dead, 1ull << i);
             // (A) inside the chunk: row i, 16 columns per thread
@@ -520,16 +544,16 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
             if (m) atomicOr(&s_mask[i], m);
         }
         __syncthreads();
-        if (tid == 0) {  // (B)
+        if (tid == 0) {  // (B): jump from survivor to survivor (the chain is as long as the number of boxes kept)
             unsigned long long sup = s_dead;
+            if (cn < 64) sup |= ~0ull << cn;
             int total = nk;
-            for (int r = 0; r < cn && total < max_det; ++r) {
-                if (!((sup >> r) & 1ull)) {
-                    s_kbox[total] = s_box[r];
-                    s_kept[total] = c0 + r;
-                    ++total;
-                    sup |= s_mask[r];
-                }
+            while (~sup != 0ull && total < max_det) {
+                const int r = __ffsll((long long)~sup) - 1;
+                s_kbox[total] = s_box[r];
+                s_kept[total] = c0 + r;
+                ++total;
+                sup |= s_mask[r] | (1ull << r);
             }
             s_nkept = total;
         }
@@ -584,6 +608,75 @@ __global__ void __launch_bounds__(256) k_nms_gather(const float* __restrict__ pr
     out_rows[(first + r) * W + col] = v;
 }
 
+// The same rows recomputed from the head feature maps the prediction was decoded from (when the caller still
+// has them): one warp per kept row, lanes over the rays - R strided loads instead of 4 + 3R, identical arithmetic
+// to k_decode*, the row written as one contiguous run.
+struct GatherFeats {
+    GridDev grid;
+    const void* feats[YCR_MAX_LEVELS];
+    int dtype, R;
+    float cs[2 * 72];
+};
+
+__global__ void __launch_bounds__(256) k_nms_gather_feats(const __grid_constant__ GatherFeats gf, int CH, ycr_nms_cfg_t cfg, NmsWs ws,
+                                                          const int* __restrict__ counts, float* __restrict__ out_rows) {
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int nk = counts[b];
+    if (blockIdx.x * 8 >= nk) return;   // block-uniform
+    __shared__ int s_first;
+    if (cfg.compact_rows) {
+        if (threadIdx.x < 32) {
+            int s = 0;
+            for (int i = threadIdx.x; i < b; i += 32) s += counts[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (threadIdx.x == 0) s_first = s;
+        }
+        __syncthreads();
+    }
+    if (r >= nk) return;
+    const int64_t first = cfg.compact_rows ? (int64_t)s_first : (int64_t)b * cfg.max_det;
+    const int R = gf.R, nc = cfg.nc, W = CH - 4 - nc + 6;
+    const int4 k = ws.kept[(int64_t)b * NMS_MAX_KEEP + r];
+    const int an = k.x;
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < YCR_MAX_LEVELS; ++q)
+        if (q < gf.grid.n_levels && an >= gf.grid.off[q]) l = q;
+    const int hw = gf.grid.h[l] * gf.grid.w[l];
+    const int al = an - gf.grid.off[l];
+    const int iy = al / gf.grid.w[l], ix = al - iy * gf.grid.w[l];
+    const float stride = gf.grid.stride[l];
+    const float ax = ((float)ix + 0.5f) * stride, ay = ((float)iy + 0.5f) * stride;
+    const int64_t f0 = (int64_t)b * (R + nc) * hw + al;
+    float* o = out_rows + (first + r) * W;
+    float minx = 3.4e38f, miny = 3.4e38f, maxx = -3.4e38f, maxy = -3.4e38f;
+    for (int i = lane; i < R; i += 32) {
+        const float dist = fmaxf(__fmul_rn(ycr_ld(gf.feats[l], f0 + (int64_t)i * hw, gf.dtype), stride), YCR_FLOOR);
+        const float x = __fadd_rn(__fmul_rn(dist, gf.cs[i]), ax);
+        const float y = __fadd_rn(__fmul_rn(dist, gf.cs[R + i]), ay);
+        minx = fminf(minx, x); maxx = fmaxf(maxx, x);
+        miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+        o[6 + i] = x;
+        o[6 + R + i] = y;
+        o[6 + 2 * R + i] = (dist > 1.f) ? 1.f : 0.f;
+    }
+#pragma unroll
+    for (int q = 16; q > 0; q >>= 1) {
+        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, q));
+        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, q));
+        maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, q));
+        maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, q));
+    }
+    if (lane == 0) {
+        o[0] = minx; o[1] = miny; o[2] = maxx; o[3] = maxy;
+        o[4] = __int_as_float(k.z);
+        o[5] = (float)k.y;
+    }
+}
+
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_ws_layout(nullptr, nullptr, B, A, cfg); }
 
 int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
@@ -607,8 +700,25 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
         k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts);
         const int maxk = cfg->max_det < NMS_MAX_KEEP ? cfg->max_det : NMS_MAX_KEEP;
         const int W = CH - 4 - cfg->nc + 6;
-        dim3 gg((maxk * W + 255) / 256, B);
-        k_nms_gather<<<gg, 256, 0, st>>>(prediction, CH, A, *cfg, ws, out_counts, out_rows);
+        const bool from_feats = cfg->grid && cfg->feats[0] && cfg->rays > 0 && cfg->rays <= 72 && CH == 4 + cfg->nc + 3 * cfg->rays;
+        if (from_feats) {
+            GatherFeats gf{};
+            gf.grid = make_grid_dev(cfg->grid);
+            for (int l = 0; l < cfg->grid->n_levels; ++l) gf.feats[l] = cfg->feats[l];
+            gf.dtype = cfg->feats_dtype;
+            gf.R = cfg->rays;
+            for (int i = 0; i < gf.R; ++i) {   // as launch_decode
+                const float deg = (float)(i * (360 / gf.R));
+                const float ang = (deg / 180.f) * (float)3.141592653589793;
+                gf.cs[i] = (float)cos((double)ang);
+                gf.cs[gf.R + i] = (float)sin((double)ang);
+            }
+            dim3 gg((maxk + 7) / 8, B);
+            k_nms_gather_feats<<<gg, 256, 0, st>>>(gf, CH, *cfg, ws, out_counts, out_rows);
+        } else {
+            dim3 gg((maxk * W + 255) / 256, B);
+            k_nms_gather<<<gg, 256, 0, st>>>(prediction, CH, A, *cfg, ws, out_counts, out_rows);
+        }
     }
     YCR_LAUNCH_CHECK();
     return YCR_OK;

@@ -33,6 +33,7 @@ def decode(feats, strides, nc: int, R: int = 36):
                                best.data_ptr(), L.stream_ptr(out.device))
     L.check(rc, "ycr_decode_dt")
     out._ycr_best_class = (best, out._version, nc)
+    out._ycr_feats = (feats, cgrid, L.DTYPE_CODE[dt], R)   # lets NMS rebuild its kept rows from R ray values each
     return out
 
 

@@ -80,14 +80,40 @@ def non_max_suppression(
         cfg.best_class = best_t.data_ptr()
     else:
         cfg.best_class = None
+    fhint = getattr(prediction, "_ycr_feats", None)
+    keep_feats = None
+    if fhint is not None and pred is prediction and hint is not None and hint[1] == prediction._version and nm == 3 * fhint[3]:
+        keep_feats, cgrid = fhint[0], fhint[1]     # (same tensor, untouched since decode wrote it)
+        for li, f in enumerate(keep_feats):
+            cfg.feats[li] = f.data_ptr()
+        cfg.grid = C.pointer(cgrid)
+        cfg.feats_dtype, cfg.rays = fhint[2], fhint[3]
     rows = torch.empty(B * max_det, 6 + nm, device=dev, dtype=torch.float32)
     counts = torch.empty(B, device=dev, dtype=torch.int32)
     rc = lib.ycr_nms(pred.data_ptr(), B, CH, A, C.byref(cfg), rows.data_ptr(), counts.data_ptr(), ws.data_ptr(),
                      ws.numel(), L.stream_ptr(dev))
     L.check(rc, "ycr_nms")
-    n = counts.tolist()
-    del cls_t, best_t
+    # the list-of-tensors return type needs the kept counts on the host: one asynchronous copy into pinned memory
+    # and one event wait (the only synchronisation of the call)
+    n = _counts_to_host(counts)
+    del cls_t, best_t, keep_feats
     return list(torch.split(rows[:sum(n)], n))
+
+
+_PINNED_COUNTS: dict = {}
+
+
+def _counts_to_host(counts):
+    B = counts.numel()
+    key = (B, str(counts.device))
+    buf = _PINNED_COUNTS.get(key)
+    if buf is None:
+        buf = _PINNED_COUNTS[key] = torch.empty(B, dtype=torch.int32).pin_memory()
+    buf.copy_(counts, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(counts.device))
+    ev.synchronize()
+    return buf.tolist()
 
 
 def resample_segments(segments, n=1000, device=None):
