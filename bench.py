@@ -318,7 +318,7 @@ def run_ours(args):
         counts = (C.c_int * 16)()
         L.check(lib.ycr_profile_end(sums, counts), "ycr_profile_end")
         names = {7: "decode", 8: "nms_filter", 9: "nms_sort", 10: "nms_suppress"}
-        emit({"quick_infer": True, "kernels_ms": {n: sums[i] / counts[i] for i, n in names.items()}})
+        emit({"quick_infer": True, "kernels_ms": {n: sums[i] / counts[i] for i, n in names.items() if counts[i]}})
         return
     for _ in range(max(args.warmup, 3)):
         step_resident()

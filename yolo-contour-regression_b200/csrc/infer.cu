@@ -404,12 +404,49 @@ __device__ unsigned nms_radix_threshold(const unsigned long long* keys, int n, i
 // When far more candidates pass the filter than max_nms keeps (the validator's conf 0.001 with multi-label:
 // ~10^5..10^6 per image), the max_nms best are selected first (radix selection on the score bits, all keys
 // tied with the threshold included) and only those are sorted.
-__global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
+__global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
+                                                   int fused_filter) {
     __shared__ unsigned long long s_keys[NMS_SORT_SMEM];
     __shared__ int s_out[4];
     const int b = blockIdx.x;
     unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
-    const int n = min(ws.count[b], ws.cap);
+    if (fused_filter) {
+        // single-label NMS on a tensor whose best class per anchor came with the decode: the conf filter
+        // (utils/ops.py:348, 386-387, 390-391) is one pass of this block over the image's 8-byte hints, so the
+        // separate filter kernel, its global counter and its re-read of the keys are not needed
+        __shared__ int s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const int2* hint = reinterpret_cast<const int2*>(cfg.best_class) + (int64_t)b * A;
+        const int nc = cfg.nc;
+        for (int an = threadIdx.x; an < A; an += blockDim.x) {
+            const int2 hv = hint[an];
+            float best = __int_as_float(hv.x);
+            int bc = hv.y;
+            if (bc < 0) {   // no hint for this anchor: scan its class rows (first maximum)
+                const float* p = pred + ((int64_t)b * CH + 4) * A + an;
+                best = -3.4e38f;
+                bc = 0;
+                for (int c = 0; c < nc; ++c) {
+                    const float v = p[(int64_t)c * A];
+                    if (v > best) { best = v; bc = c; }
+                }
+            }
+            bool ok = best > cfg.conf_thres;
+            if (ok && cfg.classes) {
+                ok = false;
+                for (int k = 0; k < cfg.n_classes; ++k) ok = ok || (cfg.classes[k] == bc);
+            }
+            if (ok) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < ws.cap) keys[slot] = ((unsigned long long)(~__float_as_uint(best)) << 32) | (unsigned)(an * nc + bc);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) ws.count[b] = s_cnt;
+        __syncthreads();
+    }
+    const int n = min(fused_filter ? *(volatile int*)&ws.count[b] : ws.count[b], ws.cap);
     if (n == 0) return;
     bool sorted = false;
     if (ws.keys2 && n > NMS_PRESEL_MIN && n > ws.nsel_cap) {
@@ -689,11 +726,14 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
     NmsWs ws;
     const size_t need = nms_ws_layout(&ws, workspace, B, A, cfg);
     if (need > workspace_bytes) { ycr_set_error("nms workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
-    YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
-    dim3 g((A + 255) / 256, B);
-    { YcrProfScope ps(YCR_T_NMS_FILTER, st); k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws); }
-    YCR_LAUNCH_CHECK();
-    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws); }
+    const int fused = (cfg->best_class && !(cfg->multi_label && cfg->nc > 1)) ? 1 : 0;
+    if (!fused) {
+        YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
+        dim3 g((A + 255) / 256, B);
+        { YcrProfScope ps(YCR_T_NMS_FILTER, st); k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws); }
+        YCR_LAUNCH_CHECK();
+    }
+    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused); }
     YCR_LAUNCH_CHECK();
     {
         YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
