@@ -67,7 +67,7 @@ def test_c2_full_batch_sampled_images_vs_oracle():
         assert torch.equal(tl[sl], ref["target_labels"])
         nz = ref["target_scores"] != 0
         assert torch.equal(ts[sl] != 0, nz)
-        assert rel_err(ts[sl][nz], ref["target_scores"][nz]) < 2e-5   # align * ov / align: three 1e-5-class factors
+        assert rel_err(ts[sl][nz], ref["target_scores"][nz]) < 1e-5
         r0 = int(mp[:b].sum())
         rows = gd[r0:r0 + int(mp[sl].sum())]
         ok = ~ref["gt_dist_ambiguous"]
@@ -211,3 +211,66 @@ def test_multi_picked_anchor_with_all_overlaps_zero_goes_to_gt0_with_real_geomet
     assert gd.shape == ref["gt_dist"].shape
     assert rel_err(gd[ok], ref["gt_dist"][ok]) < TOL
     assert rel_err(gd[0][ok[0]], ref["gt_dist"][0][ok[0]]) < TOL       # row 0 is the (GT 0, anchor 0) pair
+
+
+def test_more_than_255_gts_per_image():
+    """round 1 rejected G > 255.  The limit is now what the per-image resolution kernel can hold in shared
+    memory (815 GTs at 640 px); 300 small instances in one image against the oracle."""
+    from ycr_b200 import synth
+    dev = _dev()
+    cfg = synth.PathConfig("g300", 1, 300, 320, nc=5)
+    batch = synth.make_gts(cfg, 61)
+    batch["segments"] = [0.5 + (s - s.mean(1, keepdim=True)) * 0.35 + (s.mean(1, keepdim=True) - 0.5) for s in batch["segments"]]
+    lo, hi = batch["segments"][0].min(1)[0], batch["segments"][0].max(1)[0]
+    batch["bboxes"] = torch.cat(((lo + hi) / 2, hi - lo), 1)
+    feats = synth.make_feats_near_gt(cfg, 61, batch)
+    cpu, gpu, shapes = _assigner_inputs(cfg, feats, batch, dev)
+    assert cpu["gb"].shape[1] == 300
+    _, out = _run_assigner(cfg, gpu, shapes)
+    tl, tb, ts, mp, tgi, gd, cen, fg = [t.cpu() for t in out]
+    ref = po.assign(cpu["scores"], cpu["rays"], cpu["anc"], cpu["gl"], cpu["gb"], cpu["mask_gt"], cpu["gc"])
+    if bool(ref["certain"].all()):
+        assert torch.equal(mp, ref["mask_pos"]) and torch.equal(tgi, ref["target_gt_idx"]) and torch.equal(fg, ref["fg_mask"])
+    else:   # a near-tie somewhere among 300 crowded GTs: the undisputed part must still agree
+        assert float((mp != ref["mask_pos"]).float().mean()) < 1e-4
+    ok = ~ref["gt_dist_ambiguous"]
+    if gd.shape == ref["gt_dist"].shape:
+        assert rel_err(gd[ok], ref["gt_dist"][ok]) < TOL
+    # and beyond the limit the error names it
+    from ycr_b200.tal import TaskAlignedAssigner
+    asg = TaskAlignedAssigner(topk=10, num_classes=cfg.nc, alpha=0.5, beta=4.0)
+    G_big = 1200
+    with pytest.raises(ValueError, match="shared memory"):
+        asg(gpu["scores"], gpu["rays"], gpu["anc"], torch.zeros(1, G_big, 1, device=dev), torch.zeros(1, G_big, 4, device=dev),
+            torch.zeros(1, G_big, 1, device=dev), torch.zeros(1, G_big, 720, device=dev), gpu["st"], gpu["ss"], 0, None,
+            grid=(shapes, list(cfg.strides)))
+
+
+def test_assigner_grid_cache_distinguishes_transposed_images():
+    """a 320x256 and a 256x320 image have the same anchor count per level; the level shapes must follow the
+    image size, not a cache entry of the first call."""
+    from ycr_b200 import synth
+    from ycr_b200.tal import TaskAlignedAssigner
+    dev = _dev()
+    asg = TaskAlignedAssigner(topk=10, num_classes=4, alpha=0.5, beta=4.0)
+    g = torch.Generator().manual_seed(3)
+    for (H, W) in ((320, 256), (256, 320)):
+        shapes = [(H // s, W // s) for s in (8, 16, 32)]
+        anc, st = po.make_anchors(shapes, (8, 16, 32))
+        A = anc.shape[0]
+        t = torch.linspace(0, 2 * torch.pi, 361)[:-1]
+        cx, cy, r = 0.55 * W, 0.45 * H, 0.2 * min(H, W)
+        poly = torch.stack([cx + r * (1 + 0.2 * torch.sin(3 * t)) * torch.cos(t), cy + r * torch.sin(t)], 1)
+        seg = torch.from_numpy(synth.resample_closed((poly / torch.tensor([W, H])).numpy())) * torch.tensor([W, H])
+        box = torch.cat((seg.min(0)[0], seg.max(0)[0]))[None, None]
+        scores = torch.rand(1, A, 4, generator=g) * 0.5 + 0.1
+        rays = (torch.rand(1, A, 36, generator=g) * 3 + 1) * st
+        gl = torch.tensor([[[2.0]]])
+        mask = torch.ones(1, 1, 1)
+        gc = seg.reshape(1, 1, 720)
+        ss = [torch.full((h * w, 1), float(s)) for (h, w), s in zip(shapes, (8, 16, 32))]
+        out = asg(scores.to(dev), rays.to(dev), (anc * st).to(dev), gl.to(dev), box.to(dev), mask.to(dev), gc.to(dev),
+                  st.to(dev), [s.to(dev) for s in ss], 0, torch.tensor([float(H), float(W)], device=dev))
+        ref = po.assign(scores, rays, anc * st, gl, box, mask, gc)
+        assert torch.equal(out[3].cpu(), ref["mask_pos"]), (H, W)
+        assert torch.equal(out[7].cpu(), ref["fg_mask"]), (H, W)
