@@ -274,6 +274,19 @@ size_t ycr_nms_workspace_bytes(int B, int A, int channels, const ycr_nms_cfg_t* 
 int ycr_nms(const float* prediction, int B, int channels, int A, const ycr_nms_cfg_t* cfg, float* out_rows,
             int* out_counts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- deployment: head feature maps -> detections in one call -------------------------------- */
+
+/* What an inference plugin (TensorRT IPluginV2 enqueue, an ONNX Runtime custom op, the C++ demo of the reference's
+ * examples/) calls behind the export form of the head (nn/modules/head.py:572-574 returns the raw ray and class
+ * maps): ycr_decode + ycr_nms (single-label, as models/yolo/segment/predict.py:18 calls it) without ever writing
+ * the (B, 4+nc+3R, A) prediction tensor - best class per anchor from the class logits, conf filter and sort, boxes
+ * from the rays of the candidates only, suppression, and the kept rows [box | conf | class | x_0.. | y_0.. | valid_0..]
+ * from the rays of the kept anchors.  Rows and counts are identical to the two-call form.  cfg->nc, best_class,
+ * feats, grid are ignored (taken from the arguments); multi_label is rejected. */
+size_t ycr_detect_workspace_bytes(const ycr_grid_t* grid, int B, const ycr_nms_cfg_t* cfg);
+int ycr_detect(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, const ycr_nms_cfg_t* cfg,
+               float* out_rows, int* out_counts, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- validation: contour -> mask rasterisation and mask IoU ------------------------------ */
 
 /* Replaces the fill loop ops.process_mask has commented out (utils/ops.py:768-825, :794-809): rows are NMS output

@@ -226,3 +226,24 @@ def test_nms_uses_the_decode_by_product_only_when_valid(imgsz):
     for a, b in zip(stale, fresh):
         assert torch.equal(a, b)
     assert [d.shape[0] for d in fresh] != [d.shape[0] for d in plain]    # (the change did matter)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16], ids=["fp32", "fp16"])
+def test_detect_one_call_equals_decode_plus_nms(dt):
+    """Deployment path (ycr_detect): feature maps -> kept rows without the prediction tensor; the rows are
+    those of Segment decode + non_max_suppression, bit for bit, also with a class filter and agnostic NMS."""
+    from ycr_b200 import synth
+    from ycr_b200.head import decode
+    from ycr_b200.ops import non_max_suppression, detect
+    dev = _dev()
+    for (B, S, nc, seed) in ((4, 320, 10, 3), (16, 640, 80, 4)):
+        cfg = synth.PathConfig("det", B, 0, S, nc=nc)
+        feats = [f.to(dev).to(dt) for f in synth.make_feats(cfg, seed)]
+        for kw in (dict(conf_thres=0.25, iou_thres=0.7), dict(conf_thres=0.1, iou_thres=0.45, classes=[1, 3, 5]),
+                   dict(conf_thres=0.3, iou_thres=0.6, agnostic=True, max_det=50)):
+            want = non_max_suppression(decode(feats, cfg.strides, nc, cfg.rays), nc=nc, **kw)
+            got = detect(feats, cfg.strides, nc, cfg.rays, **kw)
+            assert [g.shape for g in got] == [w.shape for w in want]
+            assert sum(w.shape[0] for w in want) > 0
+            for g, w in zip(got, want):
+                assert torch.equal(g, w)

@@ -99,6 +99,9 @@ EXPORTS = {
                              C.c_void_p]),
     "ycr_decode_best": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "ycr_detect_workspace_bytes": (C.c_size_t, [C.POINTER(Grid), C.c_int, C.POINTER(NmsCfg)]),
+    "ycr_detect": (C.c_int, [C.POINTER(Grid), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(NmsCfg),
+                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ycr_rasterize_contours": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "ycr_mask_iou_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "ycr_mask_iou": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_float, C.c_void_p,

@@ -60,6 +60,10 @@ int launch_mask_iou(const void* m1, int dt1, const void* m2, int dt2, int N, int
 int launch_pack_targets_mapped(const float* head, int64_t hs, const float* seg, int64_t ss, const int* row_of, int B, int G,
                                float img_w, float img_h, float* out, cudaStream_t st);
 
+size_t detect_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg);
+int launch_detect(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, const ycr_nms_cfg_t* cfg,
+                  float* out_rows, int* out_counts, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 static int check_common(const ycr_grid_t* grid, const ycr_assign_cfg_t* cfg, int B, int G) {
     if (!grid || !cfg) { ycr_set_error("null grid/cfg"); return YCR_E_ARG; }
     if (grid->n_levels < 1 || grid->n_levels > YCR_MAX_LEVELS) { ycr_set_error("n_levels %d out of range", grid->n_levels); return YCR_E_ARG; }
@@ -402,6 +406,27 @@ int ycr_mask_iou(const void* mask1, int dtype1, const void* mask2, int dtype2, i
     }
     return launch_mask_iou(mask1, dtype1, mask2, dtype2, N, M, n, eps, iou, workspace, workspace_bytes,
                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ycr_detect_workspace_bytes(const ycr_grid_t* grid, int B, const ycr_nms_cfg_t* cfg) {
+    if (!grid || !cfg || B < 1 || grid->n_levels < 1 || grid->n_levels > YCR_MAX_LEVELS) return 0;
+    int A = 0;
+    for (int l = 0; l < grid->n_levels; ++l) A += grid->h[l] * grid->w[l];
+    return detect_workspace_bytes(B, A, cfg);
+}
+
+int ycr_detect(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, const ycr_nms_cfg_t* cfg,
+               float* out_rows, int* out_counts, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!grid || !feats || !cfg || !out_rows || !out_counts || !workspace) { ycr_set_error("null argument"); return YCR_E_ARG; }
+    if (grid->n_levels < 1 || grid->n_levels > YCR_MAX_LEVELS || B < 1 || nc < 1) { ycr_set_error("bad grid / B / nc"); return YCR_E_ARG; }
+    if (R < 1 || R > 72 || 360 % R) { ycr_set_error("unsupported R=%d", R); return YCR_E_ARG; }
+    if (dtype != YCR_F32 && dtype != YCR_F16 && dtype != YCR_BF16) { ycr_set_error("dtype %d: 0 f32, 1 f16, 2 bf16", dtype); return YCR_E_ARG; }
+    if (cfg->conf_thres < 0.f || cfg->conf_thres > 1.f || cfg->iou_thres < 0.f || cfg->iou_thres > 1.f) {
+        ycr_set_error("thresholds must lie in [0,1]");
+        return YCR_E_ARG;
+    }
+    return launch_detect(grid, feats, dtype, B, nc, R, cfg, out_rows, out_counts, workspace, workspace_bytes,
+                         reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -267,6 +267,38 @@ static size_t nms_ws_layout(NmsWs* ws, void* base, int B, int A, const ycr_nms_c
     return align_up(al.off, 256);
 }
 
+// The head feature maps a prediction tensor was decoded from: lets the NMS kernels recompute what they need of an
+// anchor (its box, its contour row) from the R ray values instead of reading the channel-major prediction.
+struct GatherFeats {
+    GridDev grid;
+    const void* feats[YCR_MAX_LEVELS];
+    int dtype, R;
+    float cs[2 * 72];
+};
+
+// box (min x, min y, max x, max y) of anchor `an` of image b, arithmetic identical to k_decode*
+__device__ __forceinline__ float4 box_from_feats(const GatherFeats& gf, int b, int an, int nc) {
+    int l = 0;
+#pragma unroll
+    for (int q = 1; q < YCR_MAX_LEVELS; ++q)
+        if (q < gf.grid.n_levels && an >= gf.grid.off[q]) l = q;
+    const int hw = gf.grid.h[l] * gf.grid.w[l];
+    const int al = an - gf.grid.off[l];
+    const int iy = al / gf.grid.w[l], ix = al - iy * gf.grid.w[l];
+    const float stride = gf.grid.stride[l];
+    const float ax = ((float)ix + 0.5f) * stride, ay = ((float)iy + 0.5f) * stride;
+    const int64_t f0 = (int64_t)b * (gf.R + nc) * hw + al;
+    float minx = 3.4e38f, miny = 3.4e38f, maxx = -3.4e38f, maxy = -3.4e38f;
+    for (int i = 0; i < gf.R; ++i) {
+        const float dist = fmaxf(__fmul_rn(ycr_ld(gf.feats[l], f0 + (int64_t)i * hw, gf.dtype), stride), YCR_FLOOR);
+        const float x = __fadd_rn(__fmul_rn(dist, gf.cs[i]), ax);
+        const float y = __fadd_rn(__fmul_rn(dist, gf.cs[gf.R + i]), ay);
+        minx = fminf(minx, x); maxx = fmaxf(maxx, x);
+        miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+    }
+    return make_float4(minx, miny, maxx, maxy);
+}
+
 // conf filter + best-class / multi-label expansion (utils/ops.py:348, 380-391)
 __global__ void __launch_bounds__(256) k_nms_filter(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
     const int b = blockIdx.y;
@@ -405,7 +437,7 @@ __device__ unsigned nms_radix_threshold(const unsigned long long* keys, int n, i
 // ~10^5..10^6 per image), the max_nms best are selected first (radix selection on the score bits, all keys
 // tied with the threshold included) and only those are sorted.
 __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
-                                                   int fused_filter) {
+                                                   int fused_filter, const GatherFeats* __restrict__ gfp) {
     __shared__ unsigned long long s_keys[NMS_SORT_SMEM];
     __shared__ int s_out[4];
     const int b = blockIdx.x;
@@ -492,15 +524,17 @@ __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pre
     const int nsel = min(n, ws.nsel_cap);
     const int nc = cfg.nc;
     float4* boxes = ws.boxes + (int64_t)b * ws.nsel_cap;
-    const float* p = pred + (int64_t)b * CH * A;
+    const float* p = pred ? pred + (int64_t)b * CH * A : nullptr;
     for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
         const unsigned long long k = keys[i];
         if (k == 0xFFFFFFFFFFFFFFFFull) { boxes[i] = make_float4(0.f, 0.f, -1.f, -1.f); continue; }
         const unsigned idx = (unsigned)(k & 0xFFFFFFFFull);
         const int an = idx / nc, c = idx - an * nc;
         const float off = cfg.agnostic ? 0.f : __fmul_rn((float)c, cfg.max_wh);
-        boxes[i] = make_float4(__fadd_rn(p[an], off), __fadd_rn(p[(int64_t)A + an], off),
-                               __fadd_rn(p[(int64_t)2 * A + an], off), __fadd_rn(p[(int64_t)3 * A + an], off));
+        // (the detect path has no prediction tensor: the box comes from the anchor's rays, same arithmetic)
+        const float4 bx = p ? make_float4(p[an], p[(int64_t)A + an], p[(int64_t)2 * A + an], p[(int64_t)3 * A + an])
+                            : box_from_feats(*gfp, b, an, nc);
+        boxes[i] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
     }
 }
 
@@ -645,16 +679,9 @@ __global__ void __launch_bounds__(256) k_nms_gather(const float* __restrict__ pr
     out_rows[(first + r) * W + col] = v;
 }
 
-// The same rows recomputed from the head feature maps the prediction was decoded from (when the caller still
-// has them): one warp per kept row, lanes over the rays - R strided loads instead of 4 + 3R, identical arithmetic
-// to k_decode*, the row written as one contiguous run.
-struct GatherFeats {
-    GridDev grid;
-    const void* feats[YCR_MAX_LEVELS];
-    int dtype, R;
-    float cs[2 * 72];
-};
-
+// The kept rows recomputed from the head feature maps the prediction was decoded from (when the caller still has
+// them): one warp per kept row, lanes over the rays - R strided loads instead of 4 + 3R, identical arithmetic to
+// k_decode*, the row written as one contiguous run.
 __global__ void __launch_bounds__(256) k_nms_gather_feats(const __grid_constant__ GatherFeats gf, int CH, ycr_nms_cfg_t cfg, NmsWs ws,
                                                           const int* __restrict__ counts, float* __restrict__ out_rows) {
     const int b = blockIdx.y;
@@ -714,6 +741,105 @@ __global__ void __launch_bounds__(256) k_nms_gather_feats(const __grid_constant_
     }
 }
 
+// Deployment path (ycr_detect): best class per anchor straight from the class logits - no prediction tensor.
+template <typename T>
+__global__ void __launch_bounds__(256, DCB_MINB) k_cls_best_v4(const __grid_constant__ DecodeArgs d, int2* __restrict__ best) {
+    const int A = d.grid.off[YCR_MAX_LEVELS];
+    const int b = blockIdx.y;
+    const int an = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (an >= A) return;
+    int l = 0;
+#pragma unroll
+    for (int k = 1; k < YCR_MAX_LEVELS; ++k)
+        if (k < d.grid.n_levels && an >= d.grid.off[k]) l = k;
+    const int hw = d.grid.h[l] * d.grid.w[l];
+    const int al = an - d.grid.off[l];
+    const int R = d.R, nc = d.nc;
+    const T* fc = reinterpret_cast<const T*>(d.feats[l]) + (int64_t)b * (R + nc) * hw + (int64_t)R * hw + al;
+    float bs[4] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+    int bc[4] = {0, 0, 0, 0};
+#pragma unroll 2
+    for (int c = 0; c < nc; ++c) {
+        const float4 x = YcrType<T>::ld4cs(fc + (int64_t)c * hw);
+        float4 p;   // the sigmoid of k_decode_cls_best_v4, so that scores (and ties between classes) are the same
+        p.x = 1.f / (1.f + expf(-x.x)); p.y = 1.f / (1.f + expf(-x.y));
+        p.z = 1.f / (1.f + expf(-x.z)); p.w = 1.f / (1.f + expf(-x.w));
+        if (p.x > bs[0]) { bs[0] = p.x; bc[0] = c; }
+        if (p.y > bs[1]) { bs[1] = p.y; bc[1] = c; }
+        if (p.z > bs[2]) { bs[2] = p.z; bc[2] = c; }
+        if (p.w > bs[3]) { bs[3] = p.w; bc[3] = c; }
+    }
+    int2* bo = best + (int64_t)b * A + an;
+    reinterpret_cast<int4*>(bo)[0] = make_int4(__float_as_int(bs[0]), bc[0], __float_as_int(bs[1]), bc[1]);
+    reinterpret_cast<int4*>(bo)[1] = make_int4(__float_as_int(bs[2]), bc[2], __float_as_int(bs[3]), bc[3]);
+}
+
+static void fill_gather_feats(GatherFeats& gf, const ycr_grid_t* grid, const void* const* feats, int dtype, int R) {
+    gf.grid = make_grid_dev(grid);
+    for (int l = 0; l < grid->n_levels; ++l) gf.feats[l] = feats[l];
+    gf.dtype = dtype;
+    gf.R = R;
+    for (int i = 0; i < R; ++i) {   // as launch_decode
+        const float deg = (float)(i * (360 / R));
+        const float ang = (deg / 180.f) * (float)3.141592653589793;
+        gf.cs[i] = (float)cos((double)ang);
+        gf.cs[R + i] = (float)sin((double)ang);
+    }
+}
+
+size_t detect_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) {
+    return nms_ws_layout(nullptr, nullptr, B, A, cfg) + align_up((size_t)B * A * sizeof(int2), 256) + align_up(sizeof(GatherFeats), 256);
+}
+
+// feats -> kept rows without ever writing the (B, 4+nc+3R, A) prediction: class pass, filter + sort (boxes from the
+// rays of the candidates only), suppression, rows from the rays of the kept anchors.  Single-label (predictor) form.
+int launch_detect(const ycr_grid_t* grid, const void* const* feats, int dtype, int B, int nc, int R, const ycr_nms_cfg_t* cfg,
+                  float* out_rows, int* out_counts, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (cfg->max_det < 1 || cfg->max_det > NMS_MAX_KEEP) { ycr_set_error("max_det = %d: at most %d", cfg->max_det, NMS_MAX_KEEP); return YCR_E_ARG; }
+    if (cfg->multi_label && nc > 1) { ycr_set_error("ycr_detect is the single-label (predictor) form; use ycr_decode + ycr_nms for multi_label"); return YCR_E_ARG; }
+    GatherFeats gf{};
+    fill_gather_feats(gf, grid, feats, dtype, R);
+    const int A = gf.grid.off[YCR_MAX_LEVELS];
+    for (int l = 0; l < grid->n_levels; ++l)
+        if ((grid->h[l] * grid->w[l]) % 4 || reinterpret_cast<uintptr_t>(feats[l]) % (4 * ycr_dtype_size(dtype))) {
+            ycr_set_error("ycr_detect needs level sizes H*W that are multiples of 4 and maps aligned to 4 elements");
+            return YCR_E_ARG;
+        }
+    if (detect_workspace_bytes(B, A, cfg) > workspace_bytes) { ycr_set_error("detect workspace too small"); return YCR_E_WORKSPACE; }
+    NmsWs ws;
+    char* base = reinterpret_cast<char*>(workspace);
+    const size_t off1 = nms_ws_layout(&ws, base, B, A, cfg);
+    int2* best = reinterpret_cast<int2*>(base + off1);
+    GatherFeats* gf_d = reinterpret_cast<GatherFeats*>(base + off1 + align_up((size_t)B * A * sizeof(int2), 256));
+    YCR_CUDA_CHECK(cudaMemcpyAsync(gf_d, &gf, sizeof(gf), cudaMemcpyHostToDevice, st));
+    DecodeArgs d{};
+    d.grid = gf.grid;
+    for (int l = 0; l < grid->n_levels; ++l) d.feats[l] = feats[l];
+    d.B = B; d.nc = nc; d.R = R; d.dtype = dtype;
+    ycr_nms_cfg_t c = *cfg;
+    c.best_class = best;
+    c.nc = nc;
+    const int CH = 4 + nc + 3 * R;
+    {
+        YcrProfScope ps(YCR_T_DECODE, st);
+        dim3 g((A / 4 + 255) / 256, B);
+        if (dtype == YCR_F16) k_cls_best_v4<__half><<<g, 256, 0, st>>>(d, best);
+        else if (dtype == YCR_BF16) k_cls_best_v4<__nv_bfloat16><<<g, 256, 0, st>>>(d, best);
+        else k_cls_best_v4<float><<<g, 256, 0, st>>>(d, best);
+    }
+    YCR_LAUNCH_CHECK();
+    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(nullptr, CH, A, c, ws, 1, gf_d); }
+    YCR_LAUNCH_CHECK();
+    {
+        YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
+        k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts);
+        dim3 gg((c.max_det + 7) / 8, B);
+        k_nms_gather_feats<<<gg, 256, 0, st>>>(gf, CH, c, ws, out_counts, out_rows);
+    }
+    YCR_LAUNCH_CHECK();
+    return YCR_OK;
+}
+
 size_t nms_workspace_bytes(int B, int A, const ycr_nms_cfg_t* cfg) { return nms_ws_layout(nullptr, nullptr, B, A, cfg); }
 
 int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_t* cfg, float* out_rows, int* out_counts,
@@ -733,7 +859,7 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
         { YcrProfScope ps(YCR_T_NMS_FILTER, st); k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws); }
         YCR_LAUNCH_CHECK();
     }
-    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused); }
+    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused, nullptr); }
     YCR_LAUNCH_CHECK();
     {
         YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
@@ -743,16 +869,7 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
         const bool from_feats = cfg->grid && cfg->feats[0] && cfg->rays > 0 && cfg->rays <= 72 && CH == 4 + cfg->nc + 3 * cfg->rays;
         if (from_feats) {
             GatherFeats gf{};
-            gf.grid = make_grid_dev(cfg->grid);
-            for (int l = 0; l < cfg->grid->n_levels; ++l) gf.feats[l] = cfg->feats[l];
-            gf.dtype = cfg->feats_dtype;
-            gf.R = cfg->rays;
-            for (int i = 0; i < gf.R; ++i) {   // as launch_decode
-                const float deg = (float)(i * (360 / gf.R));
-                const float ang = (deg / 180.f) * (float)3.141592653589793;
-                gf.cs[i] = (float)cos((double)ang);
-                gf.cs[gf.R + i] = (float)sin((double)ang);
-            }
+            fill_gather_feats(gf, cfg->grid, cfg->feats, cfg->feats_dtype, cfg->rays);
             dim3 gg((maxk + 7) / 8, B);
             k_nms_gather_feats<<<gg, 256, 0, st>>>(gf, CH, *cfg, ws, out_counts, out_rows);
         } else {

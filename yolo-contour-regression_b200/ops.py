@@ -100,6 +100,46 @@ def non_max_suppression(
     return list(torch.split(rows[:sum(n)], n))
 
 
+def detect(feats, strides, nc, rays=36, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, max_det=300,
+           max_nms=30000, max_wh=7680):
+    """Deployment form of `Segment.forward(eval)` + `non_max_suppression` (single-label, the predictor's call): the
+    head feature maps (fp32 / fp16 / bf16, the export branch's raw outputs nn/modules/head.py:572-574) go to the
+    kept rows in one library call that never writes the (B, 4+nc+3R, A) prediction tensor.  Same list of
+    (n_i, 6+3R) tensors, bit for bit, as the two-call form."""
+    assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
+    assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
+    L.require_cuda(*feats)
+    dev = feats[0].device
+    dt = feats[0].dtype if feats[0].dtype in L.DTYPE_CODE else torch.float32
+    feats = [f if (f.dtype == dt and f.is_contiguous()) else f.to(dt).contiguous() for f in feats]
+    B = feats[0].shape[0]
+    if feats[0].shape[1] != rays + nc:
+        raise ValueError(f"feature maps have {feats[0].shape[1]} channels, expected {rays + nc}")
+    if max_det > 1024:
+        raise ValueError(f"max_det={max_det}: at most 1024 detections per image are supported")
+    cgrid = L.make_grid([tuple(f.shape[2:]) for f in feats], [float(s) for s in strides])
+    cfg = L.NmsCfg()
+    cfg.conf_thres, cfg.iou_thres = float(conf_thres), float(iou_thres)
+    cfg.agnostic, cfg.multi_label = int(bool(agnostic)), 0
+    cfg.max_det, cfg.nc, cfg.max_nms, cfg.max_wh = int(max_det), int(nc), int(max_nms), float(max_wh)
+    cls_t = None
+    if classes is not None:
+        cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
+        cfg.classes, cfg.n_classes = cls_t.data_ptr(), cls_t.numel()
+    cfg.compact_rows = 1
+    lib = L.lib()
+    nbytes = lib.ycr_detect_workspace_bytes(C.byref(cgrid), B, C.byref(cfg))
+    ws = L.Workspace.get("detect", nbytes, dev)
+    rows = torch.empty(B * max_det, 6 + 3 * rays, device=dev, dtype=torch.float32)
+    counts = torch.empty(B, device=dev, dtype=torch.int32)
+    rc = lib.ycr_detect(C.byref(cgrid), L.ptr_array(feats), L.DTYPE_CODE[dt], B, int(nc), int(rays), C.byref(cfg),
+                        rows.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev))
+    L.check(rc, "ycr_detect")
+    n = _counts_to_host(counts)
+    del cls_t
+    return list(torch.split(rows[:sum(n)], n))
+
+
 _PINNED_COUNTS: dict = {}
 
 
