@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "assign.cu", "loss.cu", "infer.cu", "bbox_loss.cu", "resample.cu", "raster.cu"]
-HEADERS = ["common.cuh", "polar_core.cuh", "train_path.cuh"]
+HEADERS = ["common.cuh", "dtype.cuh", "polar_core.cuh", "train_path.cuh"]
 OUT = os.path.join(_HERE, "lib", "libycr_b200.so")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared"]
