@@ -124,6 +124,61 @@ def test_nms_random_vs_oracle(A, n_hot, kw):
         assert torch.equal(d.cpu(), r)
 
 
+@pytest.mark.parametrize("multi", [False, True], ids=["single_label_tranche", "multi_label_score_histogram"])
+def test_nms_leading_entries_run_out_and_the_image_is_redone(multi):
+    """More than 1024 candidates whose best-scored ones are near-duplicates of a few boxes: the entries the kernels look
+    at first (the sorted leading tranche; with multi-label over a large class space the entries above a per-image
+    score-bin limit) yield far fewer than max_det survivors, so image 0 has to be redone over everything; image 1
+    reaches max_det at once; image 2 has few candidates.  Same rows as the oracle."""
+    from ycr_b200.ops import non_max_suppression
+    dev = _dev()
+    rng = np.random.default_rng(4242)
+    nc, nm, A, B = (8, 6, 8400, 3) if multi else (3, 6, 4200, 3)
+    pred = np.zeros((B, 4 + nc + nm, A), dtype=np.float32)
+    if multi:   # every (anchor, class) pair passes conf 0.001; the background anchors are random boxes
+        xy = rng.uniform(0, 600, size=(B, 2, A)).astype(np.float32)
+        pred[:, 0:2] = xy
+        pred[:, 2:4] = xy + rng.uniform(8, 60, size=(B, 2, A)).astype(np.float32)
+        pred[:, 4:4 + nc] = rng.uniform(0.002, 0.2, size=(B, nc, A)).astype(np.float32)
+    else:
+        pred[:, 4:4 + nc] = 0.01
+
+    def put(b, idx, xyxy, cls, score):
+        pred[b, 0:4, idx] = xyxy
+        pred[b, 4 + cls, idx] = score
+
+    scores = rng.permutation(np.linspace(0.3, 0.999, 3 * 4200).astype(np.float32))   # all distinct
+    si = iter(scores)
+    # image 0: 1500 high-scored boxes in 6 tight clusters, then 900 well separated lower-scored boxes
+    centres = rng.uniform(100, 540, size=(6, 2))
+    hi = sorted([float(next(si)) for _ in range(2400)], reverse=True)
+    for k in range(1500):
+        c = centres[k % 6] + rng.uniform(-1.0, 1.0, size=2)
+        put(0, k, [c[0] - 40, c[1] - 40, c[0] + 40, c[1] + 40], 0, hi[k])
+    for k in range(900):
+        gx, gy = (k % 30) * 21 + 5, (k // 30) * 21 + 5
+        put(0, 1500 + k, [gx, gy, gx + 9, gy + 9], 1, hi[1500 + k])
+    # image 1: 2000 separated boxes (max_det reached at once)
+    for k in range(2000):
+        gx, gy = (k % 50) * 12 + 3, (k // 50) * 12 + 3
+        put(1, k, [gx, gy, gx + 8, gy + 8], 2, float(next(si)))
+    # image 2: 700 strong candidates only
+    for k in range(700):
+        gx, gy = (k % 30) * 20 + 3, (k // 30) * 20 + 3
+        put(2, k, [gx, gy, gx + 15, gy + 15], k % nc, float(next(si)))
+    pred[:, 4 + nc:] = rng.standard_normal((B, nm, A)).astype(np.float32)
+    pred = torch.from_numpy(pred)
+    kw = dict(conf_thres=0.001, iou_thres=0.6, max_det=300, multi_label=True) if multi else \
+        dict(conf_thres=0.25, iou_thres=0.6, max_det=300)
+    ref, margin = po.nms(pred, nc=nc, **kw)
+    assert margin > 1e-6
+    assert ref[0].shape[0] == 300 and int((ref[0][:, 5] == 0).sum()) <= 12     # a handful of cluster survivors, then class 1
+    dets = non_max_suppression(pred.to(dev), nc=nc, **kw)
+    assert [d.shape[0] for d in dets] == [r.shape[0] for r in ref]
+    for d, r in zip(dets, ref):
+        assert torch.equal(d.cpu(), r)
+
+
 def test_nms_argument_errors():
     from ycr_b200.ops import non_max_suppression
     dev = _dev()

@@ -240,8 +240,21 @@ struct NmsWs {
     float4* boxes;             // [B][nsel_cap] class-offset boxes in sorted order
     int4* kept;                // [B][NMS_MAX_KEEP] (anchor, class, score bits, -) of the kept rows
     unsigned long long* keys2;  // [B][presel_cap2] the preselected candidates (only when cap > NMS_PRESEL_MIN)
+    unsigned long long* tkeys;  // [B][NMS_SORT_SMEM] the sorted leading tranche (only when cap > NMS_TRANCHE)
+    int* nsorted;              // [B] entries of the sorted list the suppression may walk
+    int* tmode;                // [B] 1: that list is the tranche in tkeys and more candidates exist behind it
+    int* redo;                 // [B] 1: the tranche ran out before max_det boxes were kept -> second pass over everything
+    // score-histogram preselection (multi-label with a very low threshold: hundreds of thousands of pairs per image pass)
+    int* hist;                 // [B][NMS_HBINS] entries per score bin, best scores first (null: path off)
+    int* bsel;                 // [B] last bin the first filter pass lets through
+    int* more;                 // [B] entries that pass conf_thres but were left out by that bin limit
     int cap, cap2, nsel_cap, presel_cap2;
 };
+#define NMS_HBINS 2048
+
+#define NMS_SORT_SMEM 4096
+#define NMS_PRESEL_MIN 32768   // above this many candidates the top max_nms are selected before sorting
+#define NMS_TRANCHE 1024       // candidates sorted first; greedy NMS rarely looks further before max_det are kept
 
 static inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -257,6 +270,16 @@ static size_t nms_ws_layout(NmsWs* ws, void* base, int B, int A, const ycr_nms_c
     w.count = al.take<int>(B + 1);
     w.boxes = al.take<float4>((size_t)B * w.nsel_cap + 1);
     w.kept = al.take<int4>((size_t)B * 1024);
+    w.nsorted = al.take<int>(B);
+    w.tmode = al.take<int>(B);
+    w.redo = al.take<int>(B + 1);
+    w.tkeys = (w.cap > NMS_TRANCHE) ? al.take<unsigned long long>((size_t)B * NMS_SORT_SMEM) : nullptr;
+    w.hist = nullptr; w.bsel = nullptr; w.more = nullptr;
+    if (multi && w.cap > NMS_PRESEL_MIN) {
+        w.hist = al.take<int>((size_t)B * NMS_HBINS);
+        w.bsel = al.take<int>(B);
+        w.more = al.take<int>(B);
+    }
     w.presel_cap2 = 0;
     w.keys2 = nullptr;
     if (w.cap > 32768 && w.cap > w.nsel_cap) {
@@ -299,47 +322,139 @@ __device__ __forceinline__ float4 box_from_feats(const GatherFeats& gf, int b, i
     return make_float4(minx, miny, maxx, maxy);
 }
 
-// conf filter + best-class / multi-label expansion (utils/ops.py:348, 380-391)
-__global__ void __launch_bounds__(256) k_nms_filter(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
+// Score bin of a confidence in (0, 1]: 2^16 float steps per bin counted down from 1.0 (bin 0 = the best scores;
+// monotone, so "bin <= k" is a score threshold).  Everything below ~2^-63 lands in the last bin.
+__device__ __forceinline__ int nms_score_bin(float v) {
+    const int d = (int)(0x3F800000u - __float_as_uint(v));
+    return min(max(d >> 16, 0), NMS_HBINS - 1);
+}
+
+__device__ __forceinline__ bool nms_class_ok(const ycr_nms_cfg_t& cfg, int c) {
+    if (!cfg.classes) return true;
+    for (int k = 0; k < cfg.n_classes; ++k)
+        if (cfg.classes[k] == c) return true;
+    return false;
+}
+
+// Multi-label NMS with a very low threshold (the validator: conf 0.001) lets almost every (anchor, class) pair through -
+// 6*10^5 per image at 8400 anchors x 80 classes - while greedy NMS stops after max_det survivors, a few hundred entries
+// down the sorted list.  So the pairs are first only COUNTED per score bin (this kernel), k_nms_pick turns the counts
+// into a per-image bin limit that lets roughly NMS_TRANCHE pairs through, and the filter writes just those.  If the
+// suppression runs out of entries before max_det boxes are kept, the image is redone with the plain filter.
+__global__ void __launch_bounds__(256) k_nms_hist(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws) {
+    __shared__ int s_h[NMS_HBINS];
     const int b = blockIdx.y;
+    for (int k = threadIdx.x; k < NMS_HBINS; k += 256) s_h[k] = 0;
+    __syncthreads();
     const int an = blockIdx.x * 256 + threadIdx.x;
-    if (an >= A) return;
+    if (an < A) {
+        const float* p = pred + ((int64_t)b * CH + 4) * A + an;
+        for (int c = 0; c < cfg.nc; ++c) {
+            const float v = p[(int64_t)c * A];
+            if (v > cfg.conf_thres && nms_class_ok(cfg, c)) atomicAdd(&s_h[nms_score_bin(v)], 1);
+        }
+    }
+    __syncthreads();
+    int* h = ws.hist + (int64_t)b * NMS_HBINS;
+    for (int k = threadIdx.x; k < NMS_HBINS; k += 256)
+        if (s_h[k]) atomicAdd(&h[k], s_h[k]);
+}
+
+#define NMS_PICK (NMS_TRANCHE * 3 / 4)   // (a bin holds a few hundred entries at most: the pass usually stays below NMS_TRANCHE)
+// per image: the first bin at which the running count reaches NMS_PICK; everything, if the image has fewer than
+// NMS_SORT_SMEM entries anyway.  Also zeroes the image's entry counter for the filter that follows.
+__global__ void __launch_bounds__(256) k_nms_pick(NmsWs ws) {
+    __shared__ int s_part[256];
+    __shared__ int s_sel[2];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int* h = ws.hist + (int64_t)b * NMS_HBINS;
+    constexpr int PER = NMS_HBINS / 256;
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) local += h[t * PER + k];
+    s_part[t] = local;
+    if (t == 0) { s_sel[0] = NMS_HBINS - 1; s_sel[1] = -1; }
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {   // inclusive scan of the 256 partial sums
+        const int v = (t >= o) ? s_part[t - o] : 0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    const int total = s_part[255];
+    int cum = s_part[t] - local;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int c = h[t * PER + k];
+        if (cum < NMS_PICK && cum + c >= NMS_PICK) { s_sel[0] = t * PER + k; s_sel[1] = cum + c; }
+        cum += c;
+    }
+    __syncthreads();
+    if (t == 0) {
+        const bool all = total <= NMS_SORT_SMEM || s_sel[1] < 0;
+        ws.bsel[b] = all ? NMS_HBINS - 1 : s_sel[0];
+        ws.more[b] = all ? 0 : total - s_sel[1];
+        ws.count[b] = 0;
+    }
+}
+
+// conf filter + best-class / multi-label expansion (utils/ops.py:348, 380-391)
+// bin_limit: the per-image score-bin limits of k_nms_pick (null = everything above conf_thres); redo_only: only the
+// images whose first, limited pass ran out of entries (ws.redo), this time without the limit.
+__global__ void __launch_bounds__(256) k_nms_filter(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
+                                                    const int* __restrict__ bin_limit, int redo_only) {
+    const int b = blockIdx.y;
+    if (redo_only && !(ws.redo[b] && ws.more && ws.more[b] > 0)) return;
+    const int blim = bin_limit ? bin_limit[b] : NMS_HBINS;
+    const int an = blockIdx.x * 256 + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool live = an < A;
     const int nc = cfg.nc;
     const bool multi = cfg.multi_label && nc > 1;
-    const float* p = pred + ((int64_t)b * CH + 4) * A + an;
+    const float* p = pred + ((int64_t)b * CH + 4) * A + (live ? an : 0);
     float best = -3.4e38f;
     int bc = 0, npass = 0;
     const int2* hint = reinterpret_cast<const int2*>(cfg.best_class);
     int2 hv = make_int2(0, -1);
-    if (hint && !multi) hv = hint[(int64_t)b * A + an];
+    if (live && hint && !multi) hv = hint[(int64_t)b * A + an];
     if (hv.y >= 0) {   // the decode kernel already found the best class of this anchor
         best = __int_as_float(hv.x);
         bc = hv.y;
-    } else {
+    } else if (live) {
         for (int c = 0; c < nc; ++c) {
             const float v = p[(int64_t)c * A];
             if (v > best) { best = v; bc = c; }  // first maximum
-            npass += (v > cfg.conf_thres) ? 1 : 0;
+            // (with a bin limit the entries of filtered-out classes are left out, as k_nms_hist counted them)
+            npass += (v > cfg.conf_thres && (!bin_limit || (nms_score_bin(v) <= blim && nms_class_ok(cfg, c)))) ? 1 : 0;
         }
     }
-    if (!(best > cfg.conf_thres)) return;
+    auto class_ok = [&](int c) { return nms_class_ok(cfg, c); };
+    // entries this anchor writes; the slots of a warp are reserved with ONE atomic on the image's counter (the
+    // validator's conf 0.001 lets nearly every anchor through: one atomic per anchor serialised the whole kernel)
+    const bool pass = live && (best > cfg.conf_thres);
+    int mine = 0;
+    if (pass) mine = multi ? npass : (class_ok(bc) ? 1 : 0);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;   // (warp-uniform)
+    int base = 0;
+    if (lane == 31) base = atomicAdd(&ws.count[b], total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (mine == 0) return;
+    int slot = base + incl - mine;
     unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
-    auto class_ok = [&](int c) {
-        if (!cfg.classes) return true;
-        for (int k = 0; k < cfg.n_classes; ++k)
-            if (cfg.classes[k] == c) return true;
-        return false;
-    };
     if (!multi) {
-        if (!class_ok(bc)) return;
-        const int slot = atomicAdd(&ws.count[b], 1);
         if (slot < ws.cap)
             keys[slot] = ((unsigned long long)(~__float_as_uint(best)) << 32) | (unsigned)(an * nc + bc);
     } else {
-        int slot = atomicAdd(&ws.count[b], npass);
         for (int c = 0; c < nc; ++c) {
             const float v = p[(int64_t)c * A];
-            if (v > cfg.conf_thres) {
+            if (v > cfg.conf_thres && (!bin_limit || (nms_score_bin(v) <= blim && nms_class_ok(cfg, c)))) {
                 // entries of filtered classes keep their slot but sort to the end and are cut off
                 const bool ok = class_ok(c);
                 if (slot < ws.cap)
@@ -387,38 +502,80 @@ __device__ void bitonic_sort_pairs(unsigned long long* d, int npow2, int nthr) {
     }
 }
 
-#define NMS_SORT_SMEM 4096
-#define NMS_PRESEL_MIN 32768   // above this many candidates the top max_nms are selected before sorting
-
-// Radix selection (block-wide): among the first n keys of `keys`, find the 32-bit prefix T (the complemented
-// score bits, i.e. the high word of a key) such that fewer than `want` keys have a smaller prefix and at
-// least `want` have a prefix <= T; returns T and the number of keys with prefix <= T.  Three histogram passes
-// (12 + 12 + 8 bits) in shared memory.
+// Radix selection (block-wide, every thread of the block calls it): among the first n keys of `keys`, find a 32-bit
+// prefix T (the complemented score bits, i.e. the high word of a key) such that at least `want` keys have a prefix
+// <= T and at most ~128 more than that do, unless ties make that impossible (then the full 32 bits are decided and
+// all keys tied with T are included).  Returns T and the number of keys with prefix <= T.
+// The bits all keys share (sign, exponent and leading mantissa bits of scores in (conf, 1]) are skipped: the block
+// first reduces min and max of the prefixes, then histograms 11 bits at a time from the first bit that differs, so a
+// few thousand keys spread over 2048 bins instead of piling onto a dozen.  The crossing bin is found with a block scan.
+#define NMS_RADIX_BITS 11
 __device__ unsigned nms_radix_threshold(const unsigned long long* keys, int n, int want, int* s_hist, int* s_out,
                                         int& n_le) {
-    unsigned prefix = 0;        // bits decided so far (left-aligned in 32 bits)
-    int before = 0;             // keys whose decided bits are smaller
-    const int widths[3] = {12, 12, 8};
-    int decided = 0;
-    for (int pass = 0; pass < 3; ++pass) {
-        const int w = widths[pass], nb = 1 << w, shift = 32 - decided - w;
-        for (int i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
+    __shared__ int s_wt[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
+    if (tid == 0) { s_out[0] = -1; s_out[1] = 0; }   // (as unsigned: min starts at 0xFFFFFFFF, max at 0)
+    __syncthreads();
+    {
+        unsigned lo = 0xFFFFFFFFu, hi = 0u;
+        for (int i = tid; i < n; i += blockDim.x) {
+            const unsigned p = (unsigned)(keys[i] >> 32);
+            lo = min(lo, p);
+            hi = max(hi, p);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) {
+            atomicMin(reinterpret_cast<unsigned*>(&s_out[0]), lo);
+            atomicMax(reinterpret_cast<unsigned*>(&s_out[1]), hi);
+        }
+    }
+    __syncthreads();
+    const unsigned kmin = (unsigned)s_out[0], kmax = (unsigned)s_out[1];
+    __syncthreads();
+    if (kmin == kmax) { n_le = n; return kmax; }
+    int decided = __clz((int)(kmin ^ kmax));                  // leading bits common to all keys
+    unsigned prefix = decided ? (kmax & ~(0xFFFFFFFFu >> decided)) : 0u;
+    int before = 0;                                           // keys whose decided bits are smaller
+    n_le = n;
+    while (decided < 32) {
+        const int w = min(NMS_RADIX_BITS, 32 - decided), nb = 1 << w, shift = 32 - decided - w;
+        for (int i = tid; i < nb; i += blockDim.x) s_hist[i] = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const unsigned hi = (unsigned)(keys[i] >> 32);
-            const bool in = (decided == 0) || ((hi >> (32 - decided)) == (prefix >> (32 - decided)));
-            if (in) atomicAdd(&s_hist[(hi >> shift) & (nb - 1)], 1);
+        for (int i = tid; i < n; i += blockDim.x) {
+            const unsigned p = (unsigned)(keys[i] >> 32);
+            const bool in = (decided == 0) || ((p >> (32 - decided)) == (prefix >> (32 - decided)));
+            if (in) atomicAdd(&s_hist[(p >> shift) & (nb - 1)], 1);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int cum = before, bsel = nb - 1;
-            for (int k = 0; k < nb; ++k) {
-                if (cum + s_hist[k] >= want) { bsel = k; break; }
-                cum += s_hist[k];
+        // block scan over the bins: thread t owns bins [t*per, (t+1)*per)
+        const int per = (nb + blockDim.x - 1) / blockDim.x;
+        const int k0 = tid * per;
+        int local = 0;
+        for (int k = k0; k < min(k0 + per, nb); ++k) local += s_hist[k];
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wt[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int v = (lane < nwarp) ? s_wt[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += u;
             }
-            s_out[0] = bsel;
-            s_out[1] = cum;                      // keys strictly before the selected bin
-            s_out[2] = cum + s_hist[bsel];       // keys up to and including it
+            s_wt[lane] = v;    // inclusive totals of the warps
+        }
+        __syncthreads();
+        int cum = before + (wid ? s_wt[wid - 1] : 0) + incl - local;   // keys before this thread's first bin
+        for (int k = k0; k < min(k0 + per, nb); ++k) {
+            const int h = s_hist[k];
+            if (cum < want && cum + h >= want) { s_out[0] = k; s_out[1] = cum; s_out[2] = cum + h; }
+            cum += h;
         }
         __syncthreads();
         prefix |= (unsigned)s_out[0] << shift;
@@ -426,8 +583,10 @@ __device__ unsigned nms_radix_threshold(const unsigned long long* keys, int n, i
         n_le = s_out[2];
         decided += w;
         __syncthreads();
+        if (n_le - want <= 128) break;   // close enough: take the whole selected bin
     }
-    return prefix;
+    // undecided low bits: everything inside the selected bin counts as <= T
+    return (decided < 32) ? (prefix | (0xFFFFFFFFu >> decided)) : prefix;
 }
 
 // per image: sort candidates by (score desc, input order asc) = stable descending sort
@@ -436,13 +595,20 @@ __device__ unsigned nms_radix_threshold(const unsigned long long* keys, int n, i
 // When far more candidates pass the filter than max_nms keeps (the validator's conf 0.001 with multi-label:
 // ~10^5..10^6 per image), the max_nms best are selected first (radix selection on the score bits, all keys
 // tied with the threshold included) and only those are sorted.
+//
+// Greedy NMS walks the sorted list only until max_det boxes are kept, so with many candidates (more than NMS_TRANCHE)
+// the first pass sorts just the leading tranche: the NMS_TRANCHE best are radix-selected (ties with the threshold
+// included) and sorted in shared memory into ws.tkeys; ws.keys stays as the filter wrote it.  If the suppression runs
+// out of tranche before max_det boxes are kept it raises ws.redo[b], and pass 1 of this kernel and of the suppression
+// redo that image over all its candidates (the path every image took before) - same result either way.
 __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
-                                                   int fused_filter, const GatherFeats* __restrict__ gfp) {
+                                                   int fused_filter, const GatherFeats* __restrict__ gfp, int pass) {
     __shared__ unsigned long long s_keys[NMS_SORT_SMEM];
     __shared__ int s_out[4];
     const int b = blockIdx.x;
+    if (pass == 1 && !ws.redo[b]) return;
     unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
-    if (fused_filter) {
+    if (fused_filter && pass == 0) {
         // single-label NMS on a tensor whose best class per anchor came with the decode: the conf filter
         // (utils/ops.py:348, 386-387, 390-391) is one pass of this block over the image's 8-byte hints, so the
         // separate filter kernel, its global counter and its re-read of the keys are not needed
@@ -478,10 +644,42 @@ __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pre
         if (threadIdx.x == 0) ws.count[b] = s_cnt;
         __syncthreads();
     }
-    const int n = min(fused_filter ? *(volatile int*)&ws.count[b] : ws.count[b], ws.cap);
+    const int n = min((fused_filter && pass == 0) ? *(volatile int*)&ws.count[b] : ws.count[b], ws.cap);
+    if (threadIdx.x == 0) { ws.nsorted[b] = min(n, ws.nsel_cap); ws.tmode[b] = 0; }
     if (n == 0) return;
     bool sorted = false;
-    if (ws.keys2 && n > NMS_PRESEL_MIN && n > ws.nsel_cap) {
+    const unsigned long long* skeys = keys;      // where the sorted list ends up
+    int nsel = min(n, ws.nsel_cap);
+    if (pass == 0 && ws.tkeys && n > NMS_TRANCHE && nsel > NMS_TRANCHE) {
+        int n_le = 0;
+        // (the selection returns up to 128 keys more than asked for: ask for that many fewer, so the tranche pads to 1024)
+        const unsigned T = nms_radix_threshold(keys, n, NMS_TRANCHE - 128, reinterpret_cast<int*>(s_keys), s_out, n_le);
+        if (n_le <= NMS_SORT_SMEM && n_le < n) {   // (block-uniform) else: too many ties, or nothing behind the tranche
+            if (threadIdx.x == 0) s_out[3] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const unsigned long long k = keys[i];
+                if ((unsigned)(k >> 32) <= T) s_keys[atomicAdd(&s_out[3], 1)] = k;
+            }
+            __syncthreads();
+            const int m = s_out[3];     // == n_le
+            int mp2 = 1;
+            while (mp2 < m) mp2 <<= 1;
+            for (int i = m + threadIdx.x; i < mp2; i += blockDim.x) s_keys[i] = 0xFFFFFFFFFFFFFFFFull;
+            __syncthreads();
+            const int nthr = min((int)blockDim.x, max(32, mp2 >> 1));
+            if ((int)threadIdx.x < nthr) bitonic_sort_pairs(s_keys, mp2, nthr);
+            __syncthreads();
+            unsigned long long* tk = ws.tkeys + (int64_t)b * NMS_SORT_SMEM;
+            for (int i = threadIdx.x; i < m; i += blockDim.x) tk[i] = s_keys[i];
+            nsel = min(m, ws.nsel_cap);
+            if (threadIdx.x == 0) { ws.nsorted[b] = nsel; ws.tmode[b] = 1; }
+            skeys = tk;
+            sorted = true;
+            __syncthreads();
+        }
+    }
+    if (!sorted && ws.keys2 && n > NMS_PRESEL_MIN && n > ws.nsel_cap) {
         int n_le = 0;
         const unsigned T = nms_radix_threshold(keys, n, ws.nsel_cap, reinterpret_cast<int*>(s_keys), s_out, n_le);
         if (n_le <= ws.presel_cap2) {   // (block-uniform) otherwise too many ties: sort everything
@@ -521,12 +719,11 @@ __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pre
         }
     }
     __syncthreads();
-    const int nsel = min(n, ws.nsel_cap);
     const int nc = cfg.nc;
     float4* boxes = ws.boxes + (int64_t)b * ws.nsel_cap;
     const float* p = pred ? pred + (int64_t)b * CH * A : nullptr;
     for (int i = threadIdx.x; i < nsel; i += blockDim.x) {
-        const unsigned long long k = keys[i];
+        const unsigned long long k = skeys[i];
         if (k == 0xFFFFFFFFFFFFFFFFull) { boxes[i] = make_float4(0.f, 0.f, -1.f, -1.f); continue; }
         const unsigned idx = (unsigned)(k & 0xFFFFFFFFull);
         const int an = idx / nc, c = idx - an * nc;
@@ -563,7 +760,7 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
 // survivor are never touched.  Then the kept rows are gathered:
 // [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 418).
 __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
-                                                         float* __restrict__ out_rows, int* __restrict__ out_counts) {
+                                                         float* __restrict__ out_rows, int* __restrict__ out_counts, int pass) {
     __shared__ float4 s_kbox[NMS_MAX_KEEP];
     __shared__ int s_kept[NMS_MAX_KEEP];
     __shared__ unsigned long long s_mask[64];
@@ -571,10 +768,13 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
     __shared__ unsigned long long s_dead;
     __shared__ int s_nkept, s_cut;
     const int b = blockIdx.x, tid = threadIdx.x;
-    const int n = min(min(ws.count[b], ws.cap), ws.nsel_cap);
+    if (pass == 1 && !ws.redo[b]) return;
+    const int n_all = min(min(ws.count[b], ws.cap), ws.nsel_cap);
+    const int tmode = ws.tmode[b];
+    const int n = tmode ? min(ws.nsorted[b], n_all) : n_all;   // the sorted entries at hand (the leading tranche, or all)
     const int max_det = min(cfg.max_det, NMS_MAX_KEEP);
     const float4* boxes = ws.boxes + (int64_t)b * ws.nsel_cap;
-    const unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
+    const unsigned long long* keys = tmode ? ws.tkeys + (int64_t)b * NMS_SORT_SMEM : ws.keys + (int64_t)b * ws.cap2;
     if (tid == 0) { s_nkept = 0; s_cut = n; }
     __syncthreads();
     if (cfg.classes) {  // entries of filtered-out classes were sorted to the end: drop them
@@ -633,7 +833,17 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
     }
     __syncthreads();
     const int nk = s_nkept;
-    if (tid == 0) out_counts[b] = nk;
+    if (tid == 0) {
+        out_counts[b] = nk;
+        // the tranche ended before max_det boxes were kept and candidates remain behind it: this image is redone
+        if (pass == 0) {
+            const int more = ws.more ? ws.more[b] : 0;                       // entries the limited filter left out
+            const int n_exist = min(min(ws.count[b], ws.cap) + more, ws.nsel_cap);
+            const int again = (nk < max_det && n < n_exist) ? 1 : 0;
+            ws.redo[b] = again;
+            if (again && more > 0) ws.count[b] = 0;                          // the plain filter refills this image
+        }
+    }
     const int nc = cfg.nc;
     // hand the kept list to the gather kernel: sorted position -> (anchor, class, score)
     int4* ko = ws.kept + (int64_t)b * NMS_MAX_KEEP;
@@ -828,11 +1038,15 @@ int launch_detect(const ycr_grid_t* grid, const void* const* feats, int dtype, i
         else k_cls_best_v4<float><<<g, 256, 0, st>>>(d, best);
     }
     YCR_LAUNCH_CHECK();
-    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(nullptr, CH, A, c, ws, 1, gf_d); }
+    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(nullptr, CH, A, c, ws, 1, gf_d, 0); }
     YCR_LAUNCH_CHECK();
     {
         YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
-        k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts);
+        k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts, 0);
+        if (ws.tkeys) {   // images whose leading tranche did not yield max_det boxes (blocks of the others return at once)
+            k_nms_sort<<<B, 1024, 0, st>>>(nullptr, CH, A, c, ws, 1, gf_d, 1);
+            k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts, 1);
+        }
         dim3 gg((c.max_det + 7) / 8, B);
         k_nms_gather_feats<<<gg, 256, 0, st>>>(gf, CH, c, ws, out_counts, out_rows);
     }
@@ -853,17 +1067,33 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
     const size_t need = nms_ws_layout(&ws, workspace, B, A, cfg);
     if (need > workspace_bytes) { ycr_set_error("nms workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }
     const int fused = (cfg->best_class && !(cfg->multi_label && cfg->nc > 1)) ? 1 : 0;
+    const bool presel = !fused && ws.hist != nullptr;   // multi-label over a large (anchor, class) space: count first
     if (!fused) {
-        YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
         dim3 g((A + 255) / 256, B);
-        { YcrProfScope ps(YCR_T_NMS_FILTER, st); k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws); }
+        YcrProfScope ps(YCR_T_NMS_FILTER, st);
+        if (presel) {
+            YCR_CUDA_CHECK(cudaMemsetAsync(ws.hist, 0, (size_t)B * NMS_HBINS * sizeof(int), st));
+            k_nms_hist<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws);
+            k_nms_pick<<<B, 256, 0, st>>>(ws);
+        } else {
+            YCR_CUDA_CHECK(cudaMemsetAsync(ws.count, 0, (size_t)(B + 1) * sizeof(int), st));
+        }
+        k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws, presel ? ws.bsel : nullptr, 0);
         YCR_LAUNCH_CHECK();
     }
-    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused, nullptr); }
+    { YcrProfScope ps(YCR_T_NMS_SORT, st); k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused, nullptr, 0); }
     YCR_LAUNCH_CHECK();
     {
         YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
-        k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts);
+        k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts, 0);
+        if (ws.tkeys) {   // images whose leading tranche did not yield max_det boxes (blocks of the others return at once)
+            if (presel) {
+                dim3 g((A + 255) / 256, B);
+                k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws, nullptr, 1);
+            }
+            k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused, nullptr, 1);
+            k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts, 1);
+        }
         const int maxk = cfg->max_det < NMS_MAX_KEEP ? cfg->max_det : NMS_MAX_KEEP;
         const int W = CH - 4 - cfg->nc + 6;
         const bool from_feats = cfg->grid && cfg->feats[0] && cfg->rays > 0 && cfg->rays <= 72 && CH == 4 + cfg->nc + 3 * cfg->rays;
