@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
         AnchorPos ap{0, 0, 0, 0};
         float ax = 0.f, ay = 0.f;
         // the candidate's predicted rays and class score are requested now and used after the settlement
-        float pr[R];
+        uint32_t pr[R];      // raw words: converted where they are used, so that no load waits for its data here
+        uint32_t score_raw = 0;
         float score = 0.f;
         if (active) {
             ap = cand_anchor(a.grid, reinterpret_cast<const int4*>(&s_desc[4]), c);
@@ -332,11 +333,19 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             const int l = ap.level;
             const int64_t r0 = (int64_t)b * a.pred.rays_sb[l] + (int64_t)ap.a_local * a.pred.rays_sa[l];
             const int64_t sc = a.pred.rays_sc[l];
-#pragma unroll
-            for (int i = 0; i < R; ++i) pr[i] = ycr_ld(a.pred.rays[l], r0 + i * sc, a.dtype);
             const int label = (int)a.gt.labels[(int64_t)bg * a.gt.labels_stride];
-            score = ycr_ld(a.pred.cls[l], (int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] +
-                                          (int64_t)label * a.pred.cls_sc[l], a.dtype);
+            const int64_t si = (int64_t)b * a.pred.cls_sb[l] + (int64_t)ap.a_local * a.pred.cls_sa[l] + (int64_t)label * a.pred.cls_sc[l];
+            if (a.dtype == YCR_F32) {   // (one branch around the whole batch of loads, not one per load)
+                const uint32_t* rp = reinterpret_cast<const uint32_t*>(a.pred.rays[l]) + r0;
+#pragma unroll
+                for (int i = 0; i < R; ++i) pr[i] = rp[i * sc];
+                score_raw = reinterpret_cast<const uint32_t*>(a.pred.cls[l])[si];
+            } else {
+                const unsigned short* rp = reinterpret_cast<const unsigned short*>(a.pred.rays[l]) + r0;
+#pragma unroll
+                for (int i = 0; i < R; ++i) pr[i] = rp[i * sc];
+                score_raw = reinterpret_cast<const unsigned short*>(a.pred.cls[l])[si];
+            }
             polar_sweep<R, NT>(sm, a.pc, tid, ax, ay);
         }
         if (tid < 32) fetch_next(drawn);
@@ -358,13 +367,14 @@ __global__ void __launch_bounds__(NT) k_cand_overlaps(const __grid_constant__ As
             float smin = 0.f, smax = 0.f;
 #pragma unroll
             for (int i = 0; i < R; ++i) {
-                const float p = ycr_round_to(pr[i] * rs, a.dtype);   // the reference multiplies in the input type
+                const float p = ycr_round_to(ycr_from_raw(pr[i], a.dtype) * rs, a.dtype);   // the reference multiplies in the input type
                 const float t = sm.tv(i, tid);
                 smin += fmaxf(fminf(p, t), YCR_FLOOR);
                 smax += fmaxf(p, t);
             }
             const float ov = smin / smax;
             // `pred_scores.detach().sigmoid()` stays in the input type (utils/loss.py:861)
+            score = ycr_from_raw(score_raw, a.dtype);
             if (a.pred.cls_is_logit) score = ycr_round_to(1.f / (1.f + expf(-score)), a.dtype);
             if (ws.cand_t) {
                 float* tp = ws.cand_t + (int64_t)work * R * NT + tid;

@@ -19,6 +19,20 @@ __device__ __forceinline__ float ycr_ld(const void* p, int64_t i, int dt) {
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
 }
 
+// The same load without the conversion: the raw bits of element i (an fp32 word, or a 16-bit value zero-extended).
+// A kernel that requests values long before it uses them keeps the raw words in registers - converting at the load
+// would make every load wait for its own data - and turns them into floats with ycr_from_raw at the point of use.
+__device__ __forceinline__ uint32_t ycr_ld_raw(const void* p, int64_t i, int dt) {
+    if (dt == YCR_F32) return reinterpret_cast<const uint32_t*>(p)[i];
+    return reinterpret_cast<const unsigned short*>(p)[i];
+}
+
+__device__ __forceinline__ float ycr_from_raw(uint32_t raw, int dt) {
+    if (dt == YCR_F32) return __uint_as_float(raw);
+    if (dt == YCR_F16) return __half2float(__ushort_as_half((unsigned short)raw));
+    return __uint_as_float(raw << 16);   // a bf16 is the upper half of the fp32 with the same value
+}
+
 __device__ __forceinline__ void ycr_st(void* p, int64_t i, float v, int dt) {
     if (dt == YCR_F32) reinterpret_cast<float*>(p)[i] = v;
     else if (dt == YCR_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn(v);
