@@ -312,12 +312,30 @@ __device__ __forceinline__ float4 box_from_feats(const GatherFeats& gf, int b, i
     const float ax = ((float)ix + 0.5f) * stride, ay = ((float)iy + 0.5f) * stride;
     const int64_t f0 = (int64_t)b * (gf.R + nc) * hw + al;
     float minx = 3.4e38f, miny = 3.4e38f, maxx = -3.4e38f, maxy = -3.4e38f;
-    for (int i = 0; i < gf.R; ++i) {
-        const float dist = fmaxf(__fmul_rn(ycr_ld(gf.feats[l], f0 + (int64_t)i * hw, gf.dtype), stride), YCR_FLOOR);
-        const float x = __fadd_rn(__fmul_rn(dist, gf.cs[i]), ax);
-        const float y = __fadd_rn(__fmul_rn(dist, gf.cs[gf.R + i]), ay);
-        minx = fminf(minx, x); maxx = fmaxf(maxx, x);
-        miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+    // twelve strided loads in flight at a time (R is 36 or 72), raw words first: a conversion right behind each load
+    // would serialise their latencies
+    for (int i0 = 0; i0 < gf.R; i0 += 12) {
+        uint32_t raw[12];
+        if (gf.dtype == YCR_F32) {
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(gf.feats[l]) + f0 + (int64_t)i0 * hw;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) raw[k] = (i0 + k < gf.R) ? p[(int64_t)k * hw] : 0u;
+        } else {
+            const unsigned short* p = reinterpret_cast<const unsigned short*>(gf.feats[l]) + f0 + (int64_t)i0 * hw;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) raw[k] = (i0 + k < gf.R) ? p[(int64_t)k * hw] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int i = i0 + k;
+            if (i < gf.R) {
+                const float dist = fmaxf(__fmul_rn(ycr_from_raw(raw[k], gf.dtype), stride), YCR_FLOOR);
+                const float x = __fadd_rn(__fmul_rn(dist, gf.cs[i]), ax);
+                const float y = __fadd_rn(__fmul_rn(dist, gf.cs[gf.R + i]), ay);
+                minx = fminf(minx, x); maxx = fmaxf(maxx, x);
+                miny = fminf(miny, y); maxy = fmaxf(maxy, y);
+            }
+        }
     }
     return make_float4(minx, miny, maxx, maxy);
 }
