@@ -826,25 +826,37 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
                 dead = (inter > 0.f) && (__fdiv_rn(inter, __fsub_rn(__fadd_rn(ak, ai), inter)) > thr);
             }
             if (dead) atomicOr(&s_dead, 1ull << i);
-            // (A) inside the chunk: row i, 16 columns per thread
+            // (A) inside the chunk: row i of the (symmetric) overlap matrix, 16 columns per thread
             unsigned long long m = 0ull;
             for (int j = q * 16; j < q * 16 + 16; ++j)
-                if (j > i && j < cn && iou_gt(bi, ai, s_box[j], thr)) m |= (1ull << j);
+                if (j != i && j < cn && iou_gt(bi, ai, s_box[j], thr)) m |= (1ull << j);
             if (m) atomicOr(&s_mask[i], m);
         }
         __syncthreads();
-        if (tid == 0) {  // (B): jump from survivor to survivor (the chain is as long as the number of boxes kept)
-            unsigned long long sup = s_dead;
-            if (cn < 64) sup |= ~0ull << cn;
-            int total = nk;
-            while (~sup != 0ull && total < max_det) {
-                const int r = __ffsll((long long)~sup) - 1;
-                s_kbox[total] = s_box[r];
-                s_kept[total] = c0 + r;
-                ++total;
-                sup |= s_mask[r] | (1ull << r);
+        if (tid < 32) {
+            // (B) one warp decides the chunk, two boxes per lane (j = lane, lane + 32).  A box is removed once an
+            // EARLIER box of the chunk that overlaps it is kept, and kept once all its earlier overlappers are
+            // removed - the greedy order, resolved in rounds (the lowest undecided box is decided in every round; the
+            // usual chunk needs two or three) instead of one survivor at a time.
+            const unsigned long long dead0 = s_dead | ((cn < 64) ? (~0ull << cn) : 0ull);
+            const unsigned long long e0 = s_mask[tid] & ((1ull << tid) - 1ull);                  // earlier overlappers of box tid
+            const unsigned long long e1 = s_mask[tid + 32] & ((1ull << (tid + 32)) - 1ull);      // ... of box tid + 32
+            unsigned long long kept = 0ull, rem = dead0;
+            for (;;) {
+                const unsigned long long und = ~(kept | rem);
+                if (und == 0ull) break;
+                bool k0 = false, r0 = false, k1 = false, r1 = false;
+                if ((und >> tid) & 1ull) { r0 = (e0 & kept) != 0ull; k0 = !r0 && (e0 & ~rem) == 0ull; }
+                if ((und >> (tid + 32)) & 1ull) { r1 = (e1 & kept) != 0ull; k1 = !r1 && (e1 & ~rem) == 0ull; }
+                kept |= (unsigned long long)__ballot_sync(0xffffffffu, k0) | ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32);
+                rem |= (unsigned long long)__ballot_sync(0xffffffffu, r0) | ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
             }
-            s_nkept = total;
+            // survivors in score order behind the nk boxes kept so far, cut at max_det (utils/ops.py:408)
+            const int p0 = nk + __popcll(kept & ((1ull << tid) - 1ull));
+            const int p1 = nk + __popcll(kept & ((1ull << (tid + 32)) - 1ull));
+            if (((kept >> tid) & 1ull) && p0 < max_det) { s_kbox[p0] = s_box[tid]; s_kept[p0] = c0 + tid; }
+            if (((kept >> (tid + 32)) & 1ull) && p1 < max_det) { s_kbox[p1] = s_box[tid + 32]; s_kept[p1] = c0 + tid + 32; }
+            if (tid == 0) s_nkept = min(nk + __popcll(kept), max_det);
         }
         __syncthreads();
         if (s_nkept >= max_det) break;
