@@ -248,6 +248,8 @@ struct NmsWs {
     int* hist;                 // [B][NMS_HBINS] entries per score bin, best scores first (null: path off)
     int* bsel;                 // [B] last bin the first filter pass lets through
     int* more;                 // [B] entries that pass conf_thres but were left out by that bin limit
+    int* row_base;             // [B] first output row of image b in the compact layout (exclusive scan of the kept counts)
+    int* done_ctr;             // blocks of the final suppression launch that have finished
     int cap, cap2, nsel_cap, presel_cap2;
 };
 #define NMS_HBINS 2048
@@ -273,6 +275,8 @@ static size_t nms_ws_layout(NmsWs* ws, void* base, int B, int A, const ycr_nms_c
     w.nsorted = al.take<int>(B);
     w.tmode = al.take<int>(B);
     w.redo = al.take<int>(B + 1);
+    w.row_base = al.take<int>(B);
+    w.done_ctr = al.take<int>(4);
     w.tkeys = (w.cap > NMS_TRANCHE) ? al.take<unsigned long long>((size_t)B * NMS_SORT_SMEM) : nullptr;
     w.hist = nullptr; w.bsel = nullptr; w.more = nullptr;
     if (multi && w.cap > NMS_PRESEL_MIN) {
@@ -624,6 +628,7 @@ __global__ void __launch_bounds__(1024) k_nms_sort(const float* __restrict__ pre
     __shared__ unsigned long long s_keys[NMS_SORT_SMEM];
     __shared__ int s_out[4];
     const int b = blockIdx.x;
+    if (pass == 0 && b == 0 && threadIdx.x == 0) *ws.done_ctr = 0;
     if (pass == 1 && !ws.redo[b]) return;
     unsigned long long* keys = ws.keys + (int64_t)b * ws.cap2;
     if (fused_filter && pass == 0) {
@@ -769,6 +774,34 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
 #define NMS_NT 256
 #define NMS_MAX_KEEP 1024
 
+// Called by warp 0 of every block of the FINAL suppression launch when the block is done (its out_counts entry is
+// written): the last block to arrive turns the kept counts into the first output row of every image, so the gather
+// blocks need not each add up the counts of the images before theirs.
+__device__ __forceinline__ void nms_block_done(const NmsWs& ws, const int* out_counts, int B) {
+    const int lane = threadIdx.x & 31;
+    int last = 0;
+    if (lane == 0) {
+        __threadfence();
+        last = (atomicAdd(ws.done_ctr, 1) == B - 1) ? 1 : 0;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    int carry = 0;
+    for (int i0 = 0; i0 < B; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = (i < B) ? *(volatile const int*)&out_counts[i] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (i < B) ws.row_base[i] = carry + incl - c;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
 // per image greedy suppression over the sorted candidates, 64 at a time ("pull" form of
 // torchvision's greedy loop: a box is kept iff no EARLIER KEPT box overlaps it by more than thr):
 //   (P) the 64 boxes of the chunk are tested against every box kept so far (4 threads per box),
@@ -778,7 +811,8 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float area_a, const
 // survivor are never touched.  Then the kept rows are gathered:
 // [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 418).
 __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict__ pred, int CH, int A, ycr_nms_cfg_t cfg, NmsWs ws,
-                                                         float* __restrict__ out_rows, int* __restrict__ out_counts, int pass) {
+                                                         float* __restrict__ out_rows, int* __restrict__ out_counts, int pass,
+                                                         int final_launch) {
     __shared__ float4 s_kbox[NMS_MAX_KEEP];
     __shared__ int s_kept[NMS_MAX_KEEP];
     __shared__ unsigned long long s_mask[64];
@@ -786,7 +820,10 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
     __shared__ unsigned long long s_dead;
     __shared__ int s_nkept, s_cut;
     const int b = blockIdx.x, tid = threadIdx.x;
-    if (pass == 1 && !ws.redo[b]) return;
+    if (pass == 1 && !ws.redo[b]) {
+        if (final_launch && tid < 32) nms_block_done(ws, out_counts, gridDim.x);
+        return;
+    }
     const int n_all = min(min(ws.count[b], ws.cap), ws.nsel_cap);
     const int tmode = ws.tmode[b];
     const int n = tmode ? min(ws.nsorted[b], n_all) : n_all;   // the sorted entries at hand (the leading tranche, or all)
@@ -883,6 +920,7 @@ __global__ void __launch_bounds__(NMS_NT) k_nms_suppress(const float* __restrict
         const int an = idx / nc;
         ko[r] = make_int4(an, (int)(idx - an * nc), (int)(~(unsigned)(k >> 32)), 0);
     }
+    if (final_launch && tid < 32) nms_block_done(ws, out_counts, gridDim.x);   // (out_counts[b] was written by lane 0 above)
 }
 
 // kept rows [box xyxy | conf | class | nm mask channels] (utils/ops.py:383-387, 418): the input is
@@ -894,18 +932,8 @@ __global__ void __launch_bounds__(256) k_nms_gather(const float* __restrict__ pr
     const int nc = cfg.nc, W = CH - 4 - nc + 6;
     const int nk = counts[b];
     if ((int)blockIdx.x * 256 >= nk * W) return;   // block-uniform
-    __shared__ int s_first;
-    if (cfg.compact_rows) {   // first output row of image b = number of rows kept by the images before it
-        if (threadIdx.x < 32) {
-            int s = 0;
-            for (int i = threadIdx.x; i < b; i += 32) s += counts[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (threadIdx.x == 0) s_first = s;
-        }
-        __syncthreads();
-    }
-    const int64_t first = cfg.compact_rows ? (int64_t)s_first : (int64_t)b * cfg.max_det;
+    // compact layout: first output row of image b = rows kept by the images before it (nms_block_done)
+    const int64_t first = cfg.compact_rows ? (int64_t)ws.row_base[b] : (int64_t)b * cfg.max_det;
     const int e = blockIdx.x * 256 + threadIdx.x;
     if (e >= nk * W) return;
     const int r = e / W, col = e - r * W;
@@ -929,19 +957,8 @@ __global__ void __launch_bounds__(256) k_nms_gather_feats(const __grid_constant_
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int nk = counts[b];
     if (blockIdx.x * 8 >= nk) return;   // block-uniform
-    __shared__ int s_first;
-    if (cfg.compact_rows) {
-        if (threadIdx.x < 32) {
-            int s = 0;
-            for (int i = threadIdx.x; i < b; i += 32) s += counts[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (threadIdx.x == 0) s_first = s;
-        }
-        __syncthreads();
-    }
     if (r >= nk) return;
-    const int64_t first = cfg.compact_rows ? (int64_t)s_first : (int64_t)b * cfg.max_det;
+    const int64_t first = cfg.compact_rows ? (int64_t)ws.row_base[b] : (int64_t)b * cfg.max_det;
     const int R = gf.R, nc = cfg.nc, W = CH - 4 - nc + 6;
     const int4 k = ws.kept[(int64_t)b * NMS_MAX_KEEP + r];
     const int an = k.x;
@@ -1072,10 +1089,10 @@ int launch_detect(const ycr_grid_t* grid, const void* const* feats, int dtype, i
     YCR_LAUNCH_CHECK();
     {
         YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
-        k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts, 0);
+        k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts, 0, ws.tkeys ? 0 : 1);
         if (ws.tkeys) {   // images whose leading tranche did not yield max_det boxes (blocks of the others return at once)
             k_nms_sort<<<B, 1024, 0, st>>>(nullptr, CH, A, c, ws, 1, gf_d, 1);
-            k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts, 1);
+            k_nms_suppress<<<B, NMS_NT, 0, st>>>(nullptr, CH, A, c, ws, out_rows, out_counts, 1, 1);
         }
         dim3 gg((c.max_det + 7) / 8, B);
         k_nms_gather_feats<<<gg, 256, 0, st>>>(gf, CH, c, ws, out_counts, out_rows);
@@ -1115,14 +1132,14 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
     YCR_LAUNCH_CHECK();
     {
         YcrProfScope ps(YCR_T_NMS_SUPPRESS, st);
-        k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts, 0);
+        k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts, 0, ws.tkeys ? 0 : 1);
         if (ws.tkeys) {   // images whose leading tranche did not yield max_det boxes (blocks of the others return at once)
             if (presel) {
                 dim3 g((A + 255) / 256, B);
                 k_nms_filter<<<g, 256, 0, st>>>(prediction, CH, A, *cfg, ws, nullptr, 1);
             }
             k_nms_sort<<<B, 1024, 0, st>>>(prediction, CH, A, *cfg, ws, fused, nullptr, 1);
-            k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts, 1);
+            k_nms_suppress<<<B, NMS_NT, 0, st>>>(prediction, CH, A, *cfg, ws, out_rows, out_counts, 1, 1);
         }
         const int maxk = cfg->max_det < NMS_MAX_KEEP ? cfg->max_det : NMS_MAX_KEEP;
         const int W = CH - 4 - cfg->nc + 6;
