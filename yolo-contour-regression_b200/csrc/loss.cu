@@ -68,6 +68,9 @@ __global__ void __launch_bounds__(K5_NT) k_loss_stream(const __grid_constant__ A
     }
 }
 
+#ifndef K5V_NT
+#define K5V_NT 256   // threads per block of the vectorised kernel (four anchors per thread)
+#endif
 #ifndef K5_MINB
 #define K5_MINB 4   // 64 registers: four 256-thread blocks per SM
 #endif
@@ -86,14 +89,14 @@ __device__ __forceinline__ float bce_term(float x, float t, float gscale, float&
 }
 
 template <typename T>
-__global__ void __launch_bounds__(K5_NT, K5_MINB) k_loss_stream_v4(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
+__global__ void __launch_bounds__(K5V_NT, K5_MINB) k_loss_stream_v4(const __grid_constant__ AssignArgs a, const __grid_constant__ AssignWs ws,
                                                           const T* f0, const T* f1, const T* f2, const T* f3,
                                                           T* g0, T* g1, T* g2, T* g3, float cls_gain) {
     pdl_enter();
-    __shared__ float s_red[K5_NT / 32];
+    __shared__ float s_red[K5V_NT / 32];
     const int A = a.grid.off[YCR_MAX_LEVELS];
     const int b = blockIdx.y;
-    const int an = (blockIdx.x * K5_NT + threadIdx.x) * 4;
+    const int an = (blockIdx.x * K5V_NT + threadIdx.x) * 4;
     const int R = a.cfg.rays, nc = a.cfg.num_classes;
     float acc = 0.f;
     if (an < A) {
@@ -159,7 +162,7 @@ YCR_PRAGMA_UNROLL(K5_UNROLL)
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float v = (threadIdx.x < K5_NT / 32) ? s_red[threadIdx.x] : 0.f;
+        float v = (threadIdx.x < K5V_NT / 32) ? s_red[threadIdx.x] : 0.f;
         v = warp_sum(v);
         if (threadIdx.x == 0) ws.bce_part[blockIdx.y * gridDim.x + blockIdx.x] = v;
     }
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(1024) k_loss_finalize(AssignWs ws, int B, int 
 template <typename T>
 static cudaError_t launch_stream_v4(const AssignArgs& a, const AssignWs& ws, const void* const* f, void* const* g, dim3 grid,
                                     float cls_gain, cudaStream_t st) {
-    return ycr_launch(k_loss_stream_v4<T>, grid, dim3(K5_NT), 0, st, a, ws, reinterpret_cast<const T*>(f[0]),
+    return ycr_launch(k_loss_stream_v4<T>, grid, dim3(K5V_NT), 0, st, a, ws, reinterpret_cast<const T*>(f[0]),
                       reinterpret_cast<const T*>(f[1]), reinterpret_cast<const T*>(f[2]), reinterpret_cast<const T*>(f[3]),
                       reinterpret_cast<T*>(g[0]), reinterpret_cast<T*>(g[1]), reinterpret_cast<T*>(g[2]), reinterpret_cast<T*>(g[3]),
                       cls_gain);
@@ -227,7 +230,7 @@ int launch_loss_stream(const AssignArgs& a, const AssignWs& ws, const void* cons
     }
     int nblk;
     if (vec) {
-        dim3 grid((A / 4 + K5_NT - 1) / K5_NT, B);
+        dim3 grid((A / 4 + K5V_NT - 1) / K5V_NT, B);
         nblk = (int)(grid.x * grid.y);
         YcrProfScope ps(YCR_T_STREAM, st);
         if (a.dtype == YCR_F16) YCR_CUDA_CHECK(launch_stream_v4<__half>(a, ws, f, g, grid, lcfg.cls_gain, st));
