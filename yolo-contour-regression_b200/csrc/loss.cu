@@ -147,15 +147,26 @@ __global__ void __launch_bounds__(K5V_NT, K5_MINB) k_loss_stream_v4(const __grid
 #ifndef K5_UNROLL
 #define K5_UNROLL 4
 #endif
-YCR_PRAGMA_UNROLL(K5_UNROLL)
-        for (int c = 0; c < nc; ++c) {
-            const float4 x = YcrType<T>::ld4cs(fc + (int64_t)c * hw);
-            float4 gr;
-            acc += bce_term(x.x, (c == label[0]) ? tn[0] : 0.f, gscale, gr.x);
-            acc += bce_term(x.y, (c == label[1]) ? tn[1] : 0.f, gscale, gr.y);
-            acc += bce_term(x.z, (c == label[2]) ? tn[2] : 0.f, gscale, gr.z);
-            acc += bce_term(x.w, (c == label[3]) ? tn[3] : 0.f, gscale, gr.w);
-            if (gc) YcrType<T>::st4cs(gc + (int64_t)c * hw, gr);
+        // K5_UNROLL class rows are requested before the first of them is used: the gradient stores may alias the
+        // inputs as far as the compiler knows, so a load written behind a store stays behind it - with the plain
+        // load / compute / store loop every thread had ONE load in flight
+        for (int c0 = 0; c0 < nc; c0 += K5_UNROLL) {
+            float4 x[K5_UNROLL];
+#pragma unroll
+            for (int u = 0; u < K5_UNROLL; ++u)
+                if (c0 + u < nc) x[u] = YcrType<T>::ld4cs(fc + (int64_t)(c0 + u) * hw);
+#pragma unroll
+            for (int u = 0; u < K5_UNROLL; ++u) {
+                const int c = c0 + u;
+                if (c < nc) {
+                    float4 gr;
+                    acc += bce_term(x[u].x, (c == label[0]) ? tn[0] : 0.f, gscale, gr.x);
+                    acc += bce_term(x[u].y, (c == label[1]) ? tn[1] : 0.f, gscale, gr.y);
+                    acc += bce_term(x[u].z, (c == label[2]) ? tn[2] : 0.f, gscale, gr.z);
+                    acc += bce_term(x[u].w, (c == label[3]) ? tn[3] : 0.f, gscale, gr.w);
+                    if (gc) YcrType<T>::st4cs(gc + (int64_t)c * hw, gr);
+                }
+            }
         }
     }
     acc = warp_sum(acc);
