@@ -61,16 +61,19 @@ class _SegLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, _g_items):
+        if ctx.scaled:
+            # a second backward through the same graph (retain_graph=True): the maps were handed to autograd by the
+            # first one (and carry its upstream gradient)
+            raise RuntimeError("v8SegmentationLoss: backward through the same loss twice is not supported "
+                               "(the gradient maps are produced once, by the forward kernel)")
         grads = ctx.grads
         if grads is None:
             return (None, None, None) + (None,) * 3
+        # hand the maps over: while this node kept a reference, AccumulateGrad could not adopt a map as the .grad of a
+        # leaf input and copied it instead (three device-to-device copies, 250 MB at C2, a tenth of the step)
+        ctx.grads = None
         dev = grads[0].device
         g = g_total.detach().to(device=dev, dtype=torch.float32).contiguous()
-        if ctx.scaled:
-            # a second backward through the same graph (retain_graph=True): the stored maps already carry the
-            # first upstream gradient and would be scaled twice
-            raise RuntimeError("v8SegmentationLoss: backward through the same loss twice is not supported "
-                               "(the gradient maps are produced once, by the forward kernel)")
         ctx.scaled = True
         rc = L.lib().ycr_scale_grads_dt(C.byref(ctx.cgrid), ctx.B, ctx.channels, L.ptr_array(grads), ctx.dt, g.data_ptr(),
                                         L.stream_ptr(dev))
