@@ -212,3 +212,29 @@ def test_c2_loss_bit_identical_run_to_run():
         assert torch.equal(ref[0], cur[0]) and torch.equal(ref[1], cur[1])
         for a, b in zip(ref[2], cur[2]):
             assert torch.equal(a, b)
+
+
+def test_fresh_criteria_back_to_back_calls_do_not_disturb_each_other():
+    """The GT rows travel on a side stream into buffers a new criterion allocates on its first two calls; the caching
+    allocator may hand it a block that kernels still queued on the compute stream are using (the packed GT tensor of the
+    call before has the same size).  Calls issued back to back, without a synchronisation in between, from criteria
+    created over and over must all return the same bits."""
+    from ycr_b200.loss import v8SegmentationLoss
+    dev = _dev()
+    cfg, batch, feats = _c2(dev, seed=306)
+    want = None
+    for _ in range(6):
+        crit = v8SegmentationLoss(nc=cfg.nc, nm=cfg.rays, strides=cfg.strides, device=dev)
+        outs = []
+        for _ in range(3):                      # the host runs ahead of the device here
+            fl = [f.clone().requires_grad_(True) for f in feats]
+            total, items = crit((fl, 5, 2), batch)
+            total.backward()
+            outs.append((total.detach(), items, fl[0].grad))
+            del fl
+        got = [(float(t), i.tolist(), float(g.double().sum())) for t, i, g in outs]
+        if want is None:
+            want = got[0]
+        for g in got:
+            assert g == want
+        del crit

@@ -200,7 +200,12 @@ class v8SegmentationLoss:
             k = self._rows_turn = 1 - self._rows_turn
             if self._rows_dev[k] is None or self._rows_dev[k].numel() < stage.numel():
                 self._rows_dev[k] = torch.empty(max(stage.numel(), 64 * 726), device=dev, dtype=torch.float32)
-                self._rows_free[k] = None
+                # The allocator hands out blocks whose previous owner may still be in use by kernels queued on the
+                # compute stream (it orders reuse on THAT stream only): the copy stream must not write the new buffer
+                # before everything enqueued so far has run.
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self._rows_free[k] = ev
             rows = self._rows_dev[k][:stage.numel()]
             cs = self._copy_stream
             if self._rows_free[k] is not None:
