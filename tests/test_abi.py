@@ -60,6 +60,61 @@ def test_host_only_entry_points(lib):
     assert lib.ycr_nms_workspace_bytes(4, 8400, 192, C.byref(ncfg)) > 0
 
 
+def test_stage_targets_host_half_matches_preprocess(lib):
+    """ycr_stage_targets_h is the host half of GT packing (no CUDA call): rows, G, the (image, slot) -> row table and the
+    candidate bound of a ragged batch with an empty image; applying the table the way the packing kernel does gives the
+    oracle's preprocess (utils/loss.py:215-239) output."""
+    import numpy as np
+    from ycr_b200 import synth
+    from oracle import polar_oracle as po
+    cfg = synth.PathConfig("st", 4, 5, 160, nc=7)
+    batch = synth.make_gts(cfg, 3, ragged=True)                 # image 1 has no GT
+    bi, cls, bb = batch["batch_idx"].clone(), batch["cls"].view(-1).clone(), batch["bboxes"].clone()
+    segs = [s.contiguous() for s in batch["segments"]]
+    N, B = bi.numel(), cfg.batch
+    g = L.make_grid(cfg.level_shapes, list(cfg.strides))
+    stage = torch.full((N * 726 + B * N,), -7.0)
+    ptrs = (C.c_void_p * len(segs))(*[t.data_ptr() for t in segs])
+    nrow = (C.c_int * len(segs))(*[t.shape[0] for t in segs])
+    G, cap = C.c_int(0), C.c_int64(0)
+    rc = lib.ycr_stage_targets_h(bi.data_ptr(), cls.data_ptr(), bb.data_ptr(), ptrs, nrow, len(segs), N, B, C.byref(g),
+                                 C.c_float(160.0), C.c_float(160.0), stage.data_ptr(), C.byref(G), C.byref(cap))
+    assert rc == 0, lib.ycr_last_error()
+    counts = torch.bincount(bi.long(), minlength=B)
+    assert G.value == int(counts.max()) and int(counts[1]) == 0
+    head = stage[:N * 6].view(N, 6)
+    seg = stage[N * 6:N * 726].view(N, 720)
+    assert torch.equal(head[:, 0], bi) and torch.equal(head[:, 1], cls) and torch.equal(head[:, 2:], bb)
+    assert torch.equal(seg, torch.cat([t.reshape(-1, 720) for t in segs]))
+    row_of = np.frombuffer(stage.numpy().tobytes(), dtype=np.int32)[N * 726:N * 726 + B * G.value].reshape(B, G.value)
+    # what k_pack_targets_mapped does with the table
+    packed = torch.zeros(B, G.value, 725)
+    scale = torch.tensor([160.0, 160.0] * 360)
+    for b in range(B):
+        for sl in range(G.value):
+            n = int(row_of[b, sl])
+            assert (n >= 0) == (sl < int(counts[b]))
+            if n >= 0:
+                assert int(bi[n]) == b
+                x, y, w, h = (head[n, 2:6] * 160.0).tolist()
+                packed[b, sl, 0] = head[n, 1]
+                packed[b, sl, 1:5] = torch.tensor([x - w / 2, y - h / 2, x + w / 2, y + h / 2])
+                packed[b, sl, 5:] = seg[n] * scale
+    ref = po.pack_targets(batch, B, (160, 160))
+    assert ref.shape == packed.shape
+    assert torch.equal(packed[..., 0], ref[..., 0]) and torch.equal(packed[..., 5:], ref[..., 5:])
+    assert float((packed[..., 1:5] - ref[..., 1:5]).abs().max()) < 1e-3
+    # the bound covers the exact number of in-box anchors
+    exact = int(po.in_box_mask(po.make_anchors(cfg.level_shapes, cfg.strides)[0] * po.make_anchors(cfg.level_shapes, cfg.strides)[1],
+                               ref[..., 1:5]).sum())
+    assert exact <= cap.value
+    # malformed input: the contour blocks do not add up to the boxes
+    nrow_bad = (C.c_int * len(segs))(*[max(0, t.shape[0] - 1) for t in segs])
+    rc = lib.ycr_stage_targets_h(bi.data_ptr(), cls.data_ptr(), bb.data_ptr(), ptrs, nrow_bad, len(segs), N, B, C.byref(g),
+                                 C.c_float(160.0), C.c_float(160.0), stage.data_ptr(), C.byref(G), C.byref(cap))
+    assert rc == -1 and b"segment rows" in lib.ycr_last_error()
+
+
 def test_argument_errors_without_gpu(lib):
     g = L.make_grid([(20, 20)], [8])
     rc = lib.ycr_decode(C.byref(g), None, 1, 10, 36, None, None)
