@@ -794,7 +794,7 @@ __device__ __noinline__ float ray_target_global(const float* __restrict__ coor, 
         const float vx = coor[2 * j] - ax, vy = coor[2 * j + 1] - ay;
         m = fmaxf(m, fmaf(vx, vx, vy * vy));
     }
-    return fmaxf(sqrtf(m), YCR_FLOOR);
+    return fmaxf(dist_sqrt(m), YCR_FLOOR);
 }
 
 // K4 (gather form): when K1 kept the ray targets of every candidate, a positive's targets are just read

@@ -82,6 +82,21 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     return r;
 }
 
+// sqrt of a squared pixel distance: one MUFU.SQRT (2 ulp; the ray targets are compared at 1e-5 and every discrete
+// decision they feed is margin-checked at 2e-5) instead of the ~8 instructions of the correctly rounded sqrtf
+#ifndef YCR_FAST_SQRT
+#define YCR_FAST_SQRT 1
+#endif
+__device__ __forceinline__ float dist_sqrt(float x) {
+#if YCR_FAST_SQRT
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+
 // sorted insert with depth-2 dependency: new k_i = max(k_{i-1}, min(k_i, x))
 __device__ __forceinline__ void insert4(uint32_t& k0, uint32_t& k1, uint32_t& k2, uint32_t& k3, uint32_t x) {
     const uint32_t n3 = max(k2, min(k3, x));
@@ -291,7 +306,7 @@ __device__ __noinline__ float polar_scan_serial(const PolarSmem<R, NT>& sm, cons
         insert4(K.x, K.y, K.z, K.w, pack_pseudo(pseudo_angle(fabsf(fmaf(vy, cs.x, -vx * cs.y)), fmaf(vx, cs.x, vy * cs.y)), j));
     }
     if ((K.x >> 9) > pc.q2_gate) return YCR_FLOOR;
-    return fmaxf(sqrtf(max_dist2<R, NT>(sm, K, a)), YCR_FLOOR);
+    return fmaxf(dist_sqrt(max_dist2<R, NT>(sm, K, a)), YCR_FLOOR);
 }
 
 // Own-bin settlement of every ray of this thread; unsettled rays go to the queue of the thread's warp
@@ -330,7 +345,7 @@ YCR_UNROLL(YCR_OWN_UNROLL)
                 m = fmaxf(m, dist2_of(sm, L.y, ax, ay));
                 m = fmaxf(m, dist2_of(sm, L.z, ax, ay));
                 m = fmaxf(m, dist2_of(sm, L.w, ax, ay));
-                sm.tv(i, tid) = fmaxf(sqrtf(m), YCR_FLOOR);
+                sm.tv(i, tid) = fmaxf(dist_sqrt(m), YCR_FLOOR);
             } else {
                 unsettled = true;
             }
@@ -444,7 +459,7 @@ __device__ __forceinline__ bool polar_settle_pair(const PolarSmem<R, NT>& sm, co
     int h = 0;
     while (khi < win_hi && h < YCR_GROW) { khi = eval(++hi); ++h; }
     if (g >= YCR_GROW || h >= YCR_GROW || n_in != n_maybe || n_in != nbins) return false;
-    result = ((K.x >> 9) > pc.q2_gate) ? YCR_FLOOR : fmaxf(sqrtf(max_dist2<R, NT>(sm, K, a)), YCR_FLOOR);
+    result = ((K.x >> 9) > pc.q2_gate) ? YCR_FLOOR : fmaxf(dist_sqrt(max_dist2<R, NT>(sm, K, a)), YCR_FLOOR);
     return true;
 }
 
@@ -480,7 +495,7 @@ __device__ __forceinline__ float polar_scan_pair(const PolarSmem<R, NT>& sm, con
         w[r] = mn;
     }
     if ((W.x >> 9) > pc.q2_gate) return YCR_FLOOR;
-    return fmaxf(sqrtf(max_dist2<R, NT>(sm, W, a)), YCR_FLOOR);
+    return fmaxf(dist_sqrt(max_dist2<R, NT>(sm, W, a)), YCR_FLOOR);
 }
 
 
