@@ -41,7 +41,7 @@
 #endif
 #define YCR_MAXWIN 40  // window table entries (>= R/2 + 1 for R <= 72)
 #ifndef YCR_NBR
-#define YCR_NBR 3      // contour neighbours looked at on each side of a seed point
+#define YCR_NBR 4      // contour neighbours looked at on each side of a seed point (2: 1.006 ms, 3: 1.000, 4: 0.994, 5: 0.995)
 #endif
 
 struct PolarConst {
