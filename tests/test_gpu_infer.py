@@ -189,6 +189,15 @@ def test_nms_argument_errors():
         non_max_suppression(p, iou_thres=-0.1)
     out = non_max_suppression((p, None), nc=3)   # tuple input accepted (utils/ops.py:333-334)
     assert len(out) == 1 and out[0].shape == (0, 8)
+    # empty batch / no anchors: the reference's `[zeros((0, 6+nm))] * bs` (utils/ops.py:362)
+    assert non_max_suppression(torch.zeros(0, 9, 16, device=dev), nc=3) == []
+    out = non_max_suppression(torch.zeros(2, 9, 0, device=dev), nc=3)
+    assert len(out) == 2 and all(o.shape == (0, 8) for o in out)
+    from ycr_b200.head import decode
+    from ycr_b200.ops import detect
+    empty = [torch.zeros(0, 46, s, s, device=dev) for s in (20, 10, 5)]
+    assert decode(empty, [8, 16, 32], 10, 36).shape == (0, 4 + 10 + 108, 525)
+    assert detect(empty, [8, 16, 32], 10, 36, 0.25, 0.7) == []
 
 
 def test_segment_head_forward_contract():

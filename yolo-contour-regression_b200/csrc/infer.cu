@@ -1110,6 +1110,8 @@ int launch_nms(const float* prediction, int B, int CH, int A, const ycr_nms_cfg_
                       NMS_MAX_KEEP);
         return YCR_E_ARG;
     }
+    if (B <= 0) return YCR_OK;                               // empty batch: nothing to do (utils/ops.py:362)
+    if (A <= 0) { YCR_CUDA_CHECK(cudaMemsetAsync(out_counts, 0, (size_t)B * sizeof(int), st)); return YCR_OK; }
     NmsWs ws;
     const size_t need = nms_ws_layout(&ws, workspace, B, A, cfg);
     if (need > workspace_bytes) { ycr_set_error("nms workspace too small: need %zu have %zu", need, workspace_bytes); return YCR_E_WORKSPACE; }

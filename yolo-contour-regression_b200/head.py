@@ -28,6 +28,8 @@ def decode(feats, strides, nc: int, R: int = 36):
     # from.  It rides on the output tensor; ops.non_max_suppression uses it only if the tensor it is handed is
     # this very object and no in-place operation has touched it since (version counter).
     best = torch.empty(B, A, 2, device=feats[0].device, dtype=torch.int32)
+    if B == 0:
+        return out
     cgrid = L.make_grid(shapes, [float(s) for s in strides])
     rc = L.lib().ycr_decode_dt(C.byref(cgrid), L.ptr_array(feats), L.DTYPE_CODE[dt], B, nc, R, out.data_ptr(),
                                best.data_ptr(), L.stream_ptr(out.device))

@@ -46,6 +46,8 @@ def non_max_suppression(
     nm = CH - nc - 4
     if max_det > 1024:
         raise ValueError(f"max_det={max_det}: at most 1024 detections per image are supported")
+    if B == 0 or (A == 0 and not (labels and any(len(lb) for lb in labels))):
+        return [torch.zeros((0, 6 + nm), device=dev)] * B      # utils/ops.py:362: nothing to look at
     if labels and any(len(lb) for lb in labels):
         # apriori labels become extra candidate columns: box, a one-hot class score of 1.0, zero masks
         n_extra = max(len(lb) for lb in labels)
@@ -117,6 +119,8 @@ def detect(feats, strides, nc, rays=36, conf_thres=0.25, iou_thres=0.45, classes
         raise ValueError(f"feature maps have {feats[0].shape[1]} channels, expected {rays + nc}")
     if max_det > 1024:
         raise ValueError(f"max_det={max_det}: at most 1024 detections per image are supported")
+    if B == 0:
+        return []
     cgrid = L.make_grid([tuple(f.shape[2:]) for f in feats], [float(s) for s in strides])
     cfg = L.NmsCfg()
     cfg.conf_thres, cfg.iou_thres = float(conf_thres), float(iou_thres)
