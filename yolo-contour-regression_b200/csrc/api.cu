@@ -15,6 +15,7 @@ void ycr_set_error(const char* fmt, ...) {
 }
 
 // ---- per-kernel event timing --------------------------------------------------------------------
+#include <thread>
 #include <vector>
 #include <algorithm>
 static bool g_prof_on = false;
@@ -182,12 +183,41 @@ int ycr_stage_targets_h(const float* batch_idx_h, const float* cls_h, const floa
     float* head = staging_h;
     float* seg = staging_h + (size_t)N * 6;
     int64_t rows = 0;
+    std::vector<int64_t> first((size_t)n_seg_tensors + 1, 0);
     for (int k = 0; k < n_seg_tensors; ++k) {
         if (seg_rows_h[k] < 0 || rows + seg_rows_h[k] > N) { ycr_set_error("segment rows do not add up to the %d boxes", N); return YCR_E_ARG; }
-        memcpy(seg + (size_t)rows * 2 * YCR_C, seg_ptrs_h[k], (size_t)seg_rows_h[k] * 2 * YCR_C * sizeof(float));
+        first[(size_t)k] = rows;
         rows += seg_rows_h[k];
     }
+    first[(size_t)n_seg_tensors] = rows;
     if (rows != N) { ycr_set_error("segment rows (%lld) do not match the %d boxes", (long long)rows, N); return YCR_E_ARG; }
+    // the one pass over the contours (C2: 3.7 MB, a third of a millisecond on one core - the latency of the first step
+    // of a run, and most of this call): a few short-lived helper threads take contiguous ranges of the image blocks
+    auto copy_range = [&](int k0, int k1) {
+        for (int k = k0; k < k1; ++k)
+            memcpy(seg + (size_t)first[(size_t)k] * 2 * YCR_C, seg_ptrs_h[k], (size_t)seg_rows_h[k] * 2 * YCR_C * sizeof(float));
+    };
+    const size_t bytes = (size_t)N * 2 * YCR_C * sizeof(float);
+    int nthr = 1;
+    if (bytes >= ((size_t)1 << 20) && n_seg_tensors >= 8) {
+        static const int hw = [] {
+            const char* e = getenv("YCR_STAGE_THREADS");
+            const int want = e ? atoi(e) : 4;
+            const int have = (int)std::thread::hardware_concurrency();
+            return want < 1 ? 1 : (have > 0 && want > have ? have : want);
+        }();
+        nthr = hw;
+    }
+    if (nthr <= 1) {
+        copy_range(0, n_seg_tensors);
+    } else {
+        std::vector<std::thread> helpers;
+        helpers.reserve((size_t)nthr - 1);
+        for (int t = 1; t < nthr; ++t)
+            helpers.emplace_back(copy_range, (int)((int64_t)n_seg_tensors * t / nthr), (int)((int64_t)n_seg_tensors * (t + 1) / nthr));
+        copy_range(0, n_seg_tensors / nthr);
+        for (auto& h : helpers) h.join();
+    }
     std::vector<int> count((size_t)B, 0);
     int G = 0;
     for (int n = 0; n < N; ++n) {
