@@ -191,8 +191,10 @@ int ycr_stage_targets_h(const float* batch_idx_h, const float* cls_h, const floa
     }
     first[(size_t)n_seg_tensors] = rows;
     if (rows != N) { ycr_set_error("segment rows (%lld) do not match the %d boxes", (long long)rows, N); return YCR_E_ARG; }
-    // the one pass over the contours (C2: 3.7 MB, a third of a millisecond on one core - the latency of the first step
-    // of a run, and most of this call): a few short-lived helper threads take contiguous ranges of the image blocks
+    // the one pass over the contours (C2: 3.7 MB, a quarter of a millisecond on one core - most of this call).
+    // YCR_STAGE_THREADS=n splits it over n-1 short-lived helper threads (4: 230 -> 115 us on the GPU box's host); off by
+    // default: the path is device-bound at batch 64, and with the helpers the step measured 2.5 % SLOWER (1.240 vs
+    // 1.210 ms, twice each on one box)
     auto copy_range = [&](int k0, int k1) {
         for (int k = k0; k < k1; ++k)
             memcpy(seg + (size_t)first[(size_t)k] * 2 * YCR_C, seg_ptrs_h[k], (size_t)seg_rows_h[k] * 2 * YCR_C * sizeof(float));
@@ -202,7 +204,7 @@ int ycr_stage_targets_h(const float* batch_idx_h, const float* cls_h, const floa
     if (bytes >= ((size_t)1 << 20) && n_seg_tensors >= 8) {
         static const int hw = [] {
             const char* e = getenv("YCR_STAGE_THREADS");
-            const int want = e ? atoi(e) : 4;
+            const int want = e ? atoi(e) : 1;
             const int have = (int)std::thread::hardware_concurrency();
             return want < 1 ? 1 : (have > 0 && want > have ? have : want);
         }();
