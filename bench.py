@@ -56,6 +56,7 @@ class ClockSampler:
         self.stop_flag = False
         self.thread = None
         self.sm_max = None
+        self.period = float(os.environ.get("YCR_CLOCK_PERIOD_MS", "2")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -73,7 +74,7 @@ class ClockSampler:
                 self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.h is None:
