@@ -587,7 +587,7 @@ def run_ours(args):
         "loss_stream_hbm_frac": (stream_bytes / (kern["loss_stream"] * 1e-3) / 1e9 / peak) if "loss_stream" in kern else None,
         "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": in_bytes + gt_rows_bytes,
                 "d2h_bytes_per_step": 4, "steps": e_steps},
-        # per step: k_pack_index, k_pack_targets, k_gt_rects, k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image,
+        # per step: k_pack_targets_mapped, k_gt_rects, k_gt_setup, k_cand_overlaps, k_topk_per_gt, k_resolve_image,
         # k_positive_gather, k_loss_stream_v4, k_loss_finalize, k_scale (torch's fills and copies are not counted)
         "fp16_inputs": {"note": "same workload with fp16 head outputs (autocast, the reference's default): maps read in place, "
                                 "fp32 arithmetic, fp16 gradients",
@@ -599,7 +599,7 @@ def run_ours(args):
                     "value": world * B / (ms_dp / 1e3), "unit": "images/s", "ms_per_step": ms_dp,
                     "ms_per_step_no_allreduce": ms_dp_nosync, "allreduce_exposed_ms": max(ms_dp - ms_dp_nosync, 0.0),
                     "allreduce_bytes": dp_params * 4, "collective": "NCCL all-reduce of the head gradients (DDP buckets)"},
-        "gpu_launches": 11 * args.steps,
+        "gpu_launches": 10 * args.steps,
         "infer": {"metric": "decode+NMS images/sec", "value": inf_val, "unit": "images/s",
                   "workload": f"C3: batch {ib} @640, conf 0.25 / IoU 0.7, max_det 300, kept/img {kept:.0f}",
                   "ms_per_step": ms_inf / i_steps, "kernels_ms": ikern,
