@@ -57,7 +57,9 @@ class _SegLossFn(torch.autograd.Function):
         ctx.channels = feats[0].shape[1]
         ctx.B = B
         ctx.mark_non_differentiable(loss_out)
-        return loss_out[0].clone(), loss_out
+        # the total shares loss_out's storage (detached alias, not a tracked view: the trainer's in-place
+        # `loss *= world_size`, engine/trainer.py:365, stays legal) - a clone would be one more copy on the stream
+        return loss_out[0].detach(), loss_out
 
     @staticmethod
     def backward(ctx, g_total, _g_items):
