@@ -179,6 +179,19 @@ def test_nms_leading_entries_run_out_and_the_image_is_redone(multi):
         assert torch.equal(d.cpu(), r)
 
 
+def test_detect_packed_output_is_the_concatenated_list():
+    from ycr_b200.ops import detect
+    from ycr_b200 import synth
+    dev = _dev()
+    cfg = synth.PathConfig("dp", 3, 0, 320, nc=12)
+    feats = [f.to(dev) for f in synth.make_feats(cfg, 19)]
+    lst = detect(feats, cfg.strides, cfg.nc, cfg.rays, 0.25, 0.7)
+    rows, counts = detect(feats, cfg.strides, cfg.nc, cfg.rays, 0.25, 0.7, packed=True)
+    n = counts.tolist()
+    assert n == [d.shape[0] for d in lst] and sum(n) > 0
+    assert torch.equal(rows[:sum(n)], torch.cat(lst))
+
+
 def test_nms_argument_errors():
     from ycr_b200.ops import non_max_suppression
     dev = _dev()

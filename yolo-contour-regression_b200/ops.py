@@ -103,11 +103,13 @@ def non_max_suppression(
 
 
 def detect(feats, strides, nc, rays=36, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, max_det=300,
-           max_nms=30000, max_wh=7680):
+           max_nms=30000, max_wh=7680, packed=False):
     """Deployment form of `Segment.forward(eval)` + `non_max_suppression` (single-label, the predictor's call): the
     head feature maps (fp32 / fp16 / bf16, the export branch's raw outputs nn/modules/head.py:572-574) go to the
     kept rows in one library call that never writes the (B, 4+nc+3R, A) prediction tensor.  Same list of
-    (n_i, 6+3R) tensors, bit for bit, as the two-call form."""
+    (n_i, 6+3R) tensors, bit for bit, as the two-call form.  `packed=True` returns what the library call itself
+    produces instead - one `(sum n_i, 6+3R)` tensor with the images' rows back to back and the device tensor of the
+    B kept counts - without reading the counts on the host (no synchronisation, no B row views)."""
     assert 0 <= conf_thres <= 1, f'Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0'
     assert 0 <= iou_thres <= 1, f'Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0'
     L.require_cuda(*feats)
@@ -120,7 +122,7 @@ def detect(feats, strides, nc, rays=36, conf_thres=0.25, iou_thres=0.45, classes
     if max_det > 1024:
         raise ValueError(f"max_det={max_det}: at most 1024 detections per image are supported")
     if B == 0:
-        return []
+        return (torch.zeros(0, 6 + 3 * rays, device=dev), torch.zeros(0, dtype=torch.int32, device=dev)) if packed else []
     cgrid = L.make_grid([tuple(f.shape[2:]) for f in feats], [float(s) for s in strides])
     cfg = L.NmsCfg()
     cfg.conf_thres, cfg.iou_thres = float(conf_thres), float(iou_thres)
@@ -139,6 +141,8 @@ def detect(feats, strides, nc, rays=36, conf_thres=0.25, iou_thres=0.45, classes
     rc = lib.ycr_detect(C.byref(cgrid), L.ptr_array(feats), L.DTYPE_CODE[dt], B, int(nc), int(rays), C.byref(cfg),
                         rows.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), L.stream_ptr(dev))
     L.check(rc, "ycr_detect")
+    if packed:
+        return rows, counts   # rows past counts.sum() are unspecified
     n = _counts_to_host(counts)
     del cls_t
     return list(torch.split(rows[:sum(n)], n))
